@@ -1,0 +1,166 @@
+/*
+ * nufft_b200.h — C ABI of the B200-native NUFFT backend (libnufft_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of NonuniformFFTs.jl v0.9.6
+ *     PlanNUFFT(...)  ->  set_points!  ->  exec_type1! / exec_type2!
+ * The reference has no FFI: its GPU path is Julia multiple dispatch on
+ * `backend::KA.GPU`.  Each entry point below names the Julia method(s) whose GPU
+ * specialisation it replaces (paths relative to the reference repository).
+ * A Julia host reaches these through `ccall` (see INTEGRATION.md and
+ * nonuniformffts.jl_b200/julia/NonuniformFFTsB200.jl); the test-suite and bench
+ * reach them through Python ctypes.
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers unless the name ends in `_host`.
+ *   - Arrays are dense, column-major (Julia layout): dimension 1 is contiguous.
+ *   - Uniform data: C = ntransforms separate arrays of complex(T) with dims size(plan)
+ *     (real-data plans: first dim N1/2+1, src/plan.jl:558-562).
+ *   - Non-uniform data: C separate arrays of length Np of Z (T or complex T).
+ *   - Points: D separate arrays of T, length Np (SoA), any real value (folded to [0,2pi)).
+ *   - Work is enqueued on the plan's stream; entry points do not synchronise the device
+ *     (the reference is stream-ordered too unless synchronise=true, src/plan.jl:453-454).
+ *   - Every function returns NUFFT_SUCCESS (0) or a negative error code and never aborts;
+ *     nufft_last_error() returns a thread-local description.
+ *   - Indices exposed through the ABI are 0-based int32 (reference: 1-based Int64).
+ */
+#ifndef NUFFT_B200_H
+#define NUFFT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUFFT_B200_ABI_VERSION 1
+
+/* ---- error codes (Julia shim maps them back to the reference's exception types) ---- */
+enum {
+    NUFFT_SUCCESS = 0,
+    NUFFT_ERR_ARG = -1,         /* ArgumentError   (src/plan.jl:545-556, src/set_points.jl:35, src/NonuniformFFTs.jl:154,243) */
+    NUFFT_ERR_DIM = -2,         /* DimensionMismatch (src/NonuniformFFTs.jl:92-114, src/blocking/gpu.jl:86) */
+    NUFFT_ERR_UNSUPPORTED = -3, /* parameter combination not instantiated in this build */
+    NUFFT_ERR_CUDA = -4,        /* CUDA runtime error (sticky) */
+    NUFFT_ERR_CUFFT = -5,       /* cuFFT error */
+    NUFFT_ERR_ALLOC = -6,       /* device allocation failed */
+    NUFFT_ERR_STATE = -7        /* exec before set_points, destroyed plan, ... */
+};
+
+/* ---- enumerations ---- */
+enum { NUFFT_F32 = 0, NUFFT_F64 = 1 };
+/* src/NonuniformFFTs.jl:23-35: the four reference kernels */
+enum { NUFFT_KERNEL_KAISER_BESSEL = 0, NUFFT_KERNEL_BACKWARDS_KAISER_BESSEL = 1,
+       NUFFT_KERNEL_GAUSSIAN = 2, NUFFT_KERNEL_BSPLINE = 3 };
+/* src/Kernels/Kernels.jl:14-46 */
+enum { NUFFT_EVAL_FAST = 0, NUFFT_EVAL_DIRECT = 1 };
+/* gpu_method keyword, src/plan.jl:479, src/blocking/gpu.jl:26 */
+enum { NUFFT_METHOD_AUTO = 0, NUFFT_METHOD_GLOBAL_MEMORY = 1, NUFFT_METHOD_SHARED_MEMORY = 2 };
+
+typedef struct nufft_plan_s *nufft_plan;   /* opaque; owns all device scratch */
+
+/*
+ * Options of a plan = keyword arguments of `_PlanNUFFT` (src/plan.jl:467-482) and
+ * `PlanNUFFT` (src/plan.jl:568-599).  Zero-initialise, set struct_size = sizeof(nufft_opts),
+ * then fill; nufft_opts_default() does that with the reference defaults.
+ */
+typedef struct {
+    uint32_t struct_size;     /* = sizeof(nufft_opts) (versioning) */
+    int32_t  dim;             /* D in 1..3 */
+    int64_t  n_modes[3];      /* Ns: number of Fourier modes per dimension (src/plan.jl:467) */
+    int32_t  is_complex;      /* Z <: Complex ? 1 : 0   (non-uniform data type) */
+    int32_t  dtype;           /* NUFFT_F32 / NUFFT_F64 = real(Z) */
+    int32_t  half_support;    /* M of HalfSupport(M), default 4 (src/plan.jl:583) */
+    double   sigma;           /* oversampling factor, default 2 (src/plan.jl:573) */
+    int32_t  kernel;          /* NUFFT_KERNEL_*; reference CUDA default: KAISER_BESSEL (ext/NonuniformFFTsCUDAExt.jl:19) */
+    double   kernel_param;    /* beta (KB/BKB) or ell/dx (Gaussian); NaN = default shape rule */
+    int32_t  eval_mode;       /* NUFFT_EVAL_*; reference CUDA default: DIRECT (ext/...CUDAExt.jl:23) */
+    int32_t  ntransforms;     /* C >= 1 (src/plan.jl:570) */
+    int32_t  fftshift;        /* 1: increasing wavenumber order (complex plans only, src/plan.jl:273-280) */
+    int32_t  sort_points;     /* accepted for API parity; this backend always keeps a sorted, folded
+                                 copy of the points, results are identical either way */
+    int32_t  gpu_method;      /* NUFFT_METHOD_* */
+    int64_t  block_dims[3];   /* bin (block) dims in oversampled-grid cells; 0 = automatic */
+    int32_t  point_convention;/* 0: x in [0,2pi), e^{-ikx} type-1;  1: AbstractNFFTs convention, x in [-1/2,1/2),
+                                 opposite sign (src/abstractNFFTs.jl:150-158) */
+    int32_t  device;          /* CUDA device ordinal; -1 = current device */
+    void    *stream;          /* cudaStream_t; NULL = default stream */
+    int32_t  record_timings;  /* 1: bracket every stage with CUDA events (reference: TimerOutputs + synchronise) */
+    int32_t  spread_chunk;    /* max points per work item (0 = default); bins holding more are split */
+} nufft_opts;
+
+/*
+ * Callbacks (NUFFTCallbacks, src/plan.jl:146-164).  A compiled library cannot inline Julia
+ * closures; this is the menu that covers every callback the reference's tests use
+ * (test/callbacks.jl:17-25, test/pseudo_gpu.jl:176-223).  NULL pointer / NULL fields = default_callback.
+ */
+typedef struct {
+    uint32_t struct_size;
+    const void *nu_weights;          /* T[Np] device: v[c] *= w[n], n = ORIGINAL point index           */
+    const void *const *u_factor_sep; /* D device tables of T, len size(p)[d]: w[c] *= prod_d f_d[i_d]  */
+    const void *u_factor_dense;      /* T array of dims size(p): w[c] *= f[I]                           */
+} nufft_callbacks;
+
+/* ---- plan lifetime: PlanNUFFT constructors, src/plan.jl:467-599 ---- */
+int  nufft_opts_default(nufft_opts *opts);
+int  nufft_plan_create(nufft_plan *plan, const nufft_opts *opts);
+int  nufft_plan_destroy(nufft_plan plan);
+
+/* Base.size(p) (src/plan.jl:426), oversampled dims (src/plan.jl:485-498), ntransforms(p) (:435) */
+int  nufft_plan_shape(nufft_plan plan, int64_t size_out[3], int64_t os_dims[3], int32_t *ntransforms);
+
+/* kernel data for parity tests: shape parameter (beta or tau), dx, the (M+4)x2M polynomial
+ * coefficients [p][j] and the Fourier coefficients phihat_d (src/Kernels/*.jl). Host output. */
+int  nufft_plan_kernel_info(nufft_plan plan, int32_t d, double *shape_param, double *dx,
+                            double *cs_host /* (M+4)*2M or NULL */, double *phihat_host /* size(p)[d] or NULL */);
+
+/* ---- set_points!(p, (xs, ys, zs)): src/set_points.jl:33-52 + src/blocking/gpu.jl:73-142 ---- */
+int  nufft_set_points(nufft_plan plan, int64_t np, const void *const x[/*dim*/]);
+
+/* binning result (BlockDataGPU.pointperm / cumulative_npoints_per_block, src/blocking/gpu.jl:2-21).
+ * Device pointers owned by the plan, valid until the next set_points / destroy. */
+int  nufft_get_binning(nufft_plan plan, const int32_t **perm, const int32_t **bin_offsets,
+                       int64_t *nbins, int64_t bin_dims[3]);
+
+/* ---- exec_type1!(us_k, p, vp; callbacks): src/NonuniformFFTs.jl:148-195 ---- */
+int  nufft_exec_type1(nufft_plan plan, void *const uhat[/*C*/], const void *const vp[/*C*/],
+                      const nufft_callbacks *cb);
+/* ---- exec_type2!(vp, p, us_k; callbacks): src/NonuniformFFTs.jl:237-291 ---- */
+int  nufft_exec_type2(nufft_plan plan, void *const vp[/*C*/], const void *const uhat[/*C*/],
+                      const nufft_callbacks *cb);
+
+/*
+ * Stage-level entry points (used by the multi-GPU host layer to place a collective between
+ * stages; same stage split as the reference's timer sections, src/NonuniformFFTs.jl:157-186,246-283).
+ *   type 1:  spread  = (0) fill with zeros + (1) spreading          -> plan grid
+ *            finish  = (2) forward FFT + (3) deconvolution           -> uhat
+ *   type 2:  prepare = (0)+(1) zero-pad/deconvolve + (2) backward FFT -> plan grid
+ *            interp  = (3) interpolation                              -> vp
+ */
+int  nufft_type1_spread(nufft_plan plan, const void *const vp[], const nufft_callbacks *cb);
+int  nufft_type1_finish(nufft_plan plan, void *const uhat[], const nufft_callbacks *cb);
+int  nufft_type2_prepare(nufft_plan plan, const void *const uhat[], const nufft_callbacks *cb);
+int  nufft_type2_interp(nufft_plan plan, void *const vp[], const nufft_callbacks *cb);
+
+/* plan-owned oversampled physical grid `us` (PlanNUFFT.data.us, src/plan.jl:3-31): C contiguous
+ * arrays of Z with dims os_dims.  bytes_per_transform = prod(os_dims) * sizeof(Z). */
+int  nufft_get_grid(nufft_plan plan, void **grid, size_t *bytes_per_transform);
+
+/* per-stage device times in ms of the most recent calls (record_timings=1), reference stage names:
+ *  [0] set_points  [1] t1 fill zeros  [2] t1 spreading  [3] t1 forward FFT  [4] t1 deconvolution
+ *  [5] t2 zero-pad+deconvolution  [6] t2 backward FFT  [7] t2 interpolation  [8..15] reserved */
+int  nufft_get_timings(nufft_plan plan, float ms[16]);
+
+/* counts kernel launches issued by this library on the calling thread since the last reset */
+int64_t nufft_launch_count(int reset);
+
+/* Base.show(::PlanNUFFT) (src/plan.jl:362-392) + chosen tile/CTA shapes and bin statistics */
+int  nufft_describe(nufft_plan plan, char *buf, size_t buflen);
+
+const char *nufft_last_error(void);
+int  nufft_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUFFT_B200_H */

@@ -1,0 +1,16 @@
+"""nonuniformffts.jl_b200 — B200-native NUFFT backend behind the NonuniformFFTs.jl API.
+
+The directory name contains a dot, so import it through the repo-root shim: ``import nufft_b200``.
+Only what the hot path needs lives here: ``csrc/`` (CUDA kernels + C ABI), the ctypes binding
+(``_lib``), the host-side mirror of the reference interface (``plan``), the multi-GPU host layer
+(``distributed``) and the Julia ccall shim (``julia/``).
+"""
+from .plan import (ArgumentError, BackwardsKaiserBesselKernel, BSplineKernel, DimensionMismatch, Direct,
+                   FastApproximation, GaussianKernel, HalfSupport, KaiserBesselKernel, NUFFTCallbacks, NUFFTError,
+                   PlanNUFFT, exec_type1, exec_type2, launch_count, set_points)
+
+__all__ = [
+    "PlanNUFFT", "set_points", "exec_type1", "exec_type2", "HalfSupport", "NUFFTCallbacks",
+    "KaiserBesselKernel", "BackwardsKaiserBesselKernel", "GaussianKernel", "BSplineKernel",
+    "Direct", "FastApproximation", "ArgumentError", "DimensionMismatch", "NUFFTError", "launch_count",
+]

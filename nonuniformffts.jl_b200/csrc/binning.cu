@@ -1,0 +1,406 @@
+// binning.cu — K-bin: set_points! on the GPU.
+//
+// Replaces src/blocking/gpu.jl:73-212 (assign_blocks_kernel!, AK.accumulate!, sortperm_kernel!,
+// permute_kernel!) and src/set_points.jl:33-52.
+//
+// The reference ranks points inside a bin with an atomic counter, so its intra-bin order is
+// non-deterministic.  Here the (bin id -> point index) pairs go through a stable LSD radix sort
+// restricted to ceil(log2(nbins)) key bits, which yields exactly the order of the reference's
+// single-thread counting sort (src/blocking/cpu.jl:73-111): deterministic and bit-comparable.
+//
+// Kernels
+//   bin_keys_kernel      fold + point_to_cell + block_index -> 32-bit key, bin histogram (warp-aggregated atomics)
+//   radix_hist_kernel    per-CTA digit histogram (8-bit digits)
+//   scan kernels         exclusive prefix sum (digit-major histogram; bin offsets; work items)
+//   radix_scatter_kernel stable scatter (warp match_any ranks + per-warp digit counters)
+//   gather_points_kernel sorted, folded copy of the coordinates (coalesced reads in spread/interp)
+//   work_items_kernel    items per bin = ceil(count / chunk) (bins over `chunk` points are split)
+#include "common.cuh"
+#include "kernel_eval.cuh"
+
+namespace nufft {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+struct BinGeom {
+    int D;
+    int N[3];
+    int B[3];
+    int nb[3];
+    int convention;
+};
+
+// ---- keys --------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
+                uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < np; base += stride) {
+        const int64_t i = base + threadIdx.x;
+        const bool valid = i < np;
+        uint32_t key = 0xffffffffu;
+        if (valid) {
+            T r;
+            int c = point_to_cell0<T>(fold_point<T>(x0[i], g.convention), g.N[0], r);
+            uint32_t k = (uint32_t)(c / g.B[0]);
+            if (g.D > 1) {
+                c = point_to_cell0<T>(fold_point<T>(x1[i], g.convention), g.N[1], r);
+                k += (uint32_t)(c / g.B[1]) * (uint32_t)g.nb[0];
+            }
+            if (g.D > 2) {
+                c = point_to_cell0<T>(fold_point<T>(x2[i], g.convention), g.N[2], r);
+                k += (uint32_t)(c / g.B[2]) * (uint32_t)(g.nb[0] * g.nb[1]);
+            }
+            key = k;
+            keys[i] = key;
+        }
+        // warp-aggregated histogram: one atomic per distinct key in the warp (clustered inputs)
+        const unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned peers = __match_any_sync(active, key);
+            if (lane == __ffs(peers) - 1) atomicAdd(&bin_count[key + 1], (uint32_t)__popc(peers));
+        }
+    }
+}
+
+// ---- exclusive scan (uint32, in place), three kernels -------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *smem /*>= 32*/, uint32_t &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        smem[lane] = winc - w;          // exclusive warp offsets
+        if (lane == 31) smem[32] = winc; // block total
+    }
+    __syncthreads();
+    const uint32_t res = smem[warp] + inc - v;
+    total = smem[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint32_t *__restrict__ data, int64_t n, uint32_t *__restrict__ sums)
+{
+    __shared__ uint32_t sm[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) s += data[i];
+    }
+    uint32_t total;
+    block_exclusive_scan(s, sm, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of the block sums (loops over chunks, carries a running prefix)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t *__restrict__ sums, int64_t m)
+{
+    __shared__ uint32_t sm[33];
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < m; base += SCAN_THREADS) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = (i < m) ? sums[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, sm, total);
+        if (i < m) sums[i] = ex + carry;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t *__restrict__ data, int64_t n, const uint32_t *__restrict__ sums, int inclusive)
+{
+    __shared__ uint32_t sm[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;   // blocked arrangement
+    uint32_t v[SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? data[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(s, sm, total) + sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) data[base + k] = inclusive ? run + v[k] : run;
+        run += v[k];
+    }
+}
+
+int scan_u32(Plan &p, uint32_t *data, int64_t n, bool inclusive)
+{
+    if (n <= 0) return NUFFT_SUCCESS;
+    const int64_t nblk = cdiv(n, SCAN_TILE);
+    if ((size_t)nblk > p.scan_tmp_cap) {
+        if (p.d_scan_tmp) cudaFree(p.d_scan_tmp);
+        p.scan_tmp_cap = (size_t)nblk * 2 + 64;
+        CUDA_TRY(cudaMalloc(&p.d_scan_tmp, p.scan_tmp_cap * sizeof(uint32_t)));
+    }
+    scan_reduce_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, p.stream>>>(data, n, p.d_scan_tmp);
+    NUFFT_COUNT_LAUNCH();
+    scan_sums_kernel<<<1, SCAN_THREADS, 0, p.stream>>>(p.d_scan_tmp, nblk);
+    NUFFT_COUNT_LAUNCH();
+    scan_apply_kernel<<<(unsigned)nblk, SCAN_THREADS, 0, p.stream>>>(data, n, p.d_scan_tmp, inclusive ? 1 : 0);
+    NUFFT_COUNT_LAUNCH();
+    CUDA_TRY(cudaGetLastError());
+    return NUFFT_SUCCESS;
+}
+
+// ---- radix sort passes -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ hist, int nblk)
+{
+    __shared__ uint32_t h[RADIX];
+    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) h[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+#pragma unroll 4
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int64_t i = base + (int64_t)k * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[(size_t)i * nblk + blockIdx.x] = h[i];
+}
+
+// Stable scatter.  Order inside a CTA tile: warp-major, then iteration k, then lane (== index order).
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
+                     const uint32_t *__restrict__ hist_scanned, int nblk,
+                     uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out)
+{
+    __shared__ uint32_t warp_cnt[SORT_WARPS][RADIX];
+    __shared__ uint32_t digit_base[RADIX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)warp * (32 * SORT_ITEMS);
+    uint32_t key[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        key[k] = valid ? keys_in[i] : 0u;
+        const uint32_t digit = (key[k] >> shift) & (RADIX - 1);
+        const uint32_t tag = valid ? digit : (uint32_t)(RADIX + lane);   // invalid lanes never match anyone
+        const unsigned peers = __match_any_sync(0xffffffffu, tag);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pre = 0;
+        if (lane == leader && valid) {
+            pre = warp_cnt[warp][digit];
+            warp_cnt[warp][digit] = pre + __popc(peers);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rank[k] = pre + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive scan over the warps of this CTA + global base of (digit, CTA)
+    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = warp_cnt[w][d];
+            warp_cnt[w][d] = run;
+            run += t;
+        }
+        digit_base[d] = hist_scanned[(size_t)d * nblk + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (key[k] >> shift) & (RADIX - 1);
+            const uint32_t pos = digit_base[digit] + warp_cnt[warp][digit] + rank[k];
+            if (!LAST) keys_out[pos] = key[k];
+            vals_out[pos] = FIRST ? (int32_t)i : vals_in[i];
+        }
+    }
+}
+
+// ---- sorted, folded copy of the points ---------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_points_kernel(int D, int convention, int64_t np, const int32_t *__restrict__ perm,
+                     const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
+                     T *__restrict__ y0, T *__restrict__ y1, T *__restrict__ y2)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= np) return;
+    const int32_t i = perm[k];
+    y0[k] = fold_point<T>(x0[i], convention);
+    if (D > 1) y1[k] = fold_point<T>(x1[i], convention);
+    if (D > 2) y2[k] = fold_point<T>(x2[i], convention);
+}
+
+// bin_count[b+1] holds the count of bin b -> items[b+1] = ceil(count / chunk); [0] = 0
+__global__ void work_items_kernel(const int32_t *__restrict__ bin_offsets, int64_t nbins, int chunk, int32_t *__restrict__ items)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) items[0] = 0;
+    if (b < nbins) {
+        const int32_t c = bin_offsets[b + 1] - bin_offsets[b];
+        items[b + 1] = (c + chunk - 1) / chunk;
+    }
+}
+
+// identity permutation when there is a single bin and nothing to sort
+__global__ void iota_kernel(int32_t *v, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+
+static int ensure_capacity(Plan &p, int64_t np)
+{
+    if (np <= p.cap) return NUFFT_SUCCESS;
+    auto f = [](auto *&ptr) { if (ptr) { cudaFree((void *)ptr); ptr = nullptr; } };
+    f(p.d_keys[0]); f(p.d_keys[1]); f(p.d_vals[0]); f(p.d_vals[1]);
+    for (int d = 0; d < 3; ++d) f(p.d_xs[d]);
+    const int64_t cap = np + np / 8 + 1024;   // head-room: no reallocation when Np fluctuates
+    p.cap = 0;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&p.d_keys[i], (size_t)cap * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&p.d_vals[i], (size_t)cap * sizeof(int32_t));
+    }
+    for (int d = 0; d < p.D && e == cudaSuccess; ++d) e = cudaMalloc(&p.d_xs[d], (size_t)cap * p.real_bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cannot allocate point buffers for %lld points", (long long)np);
+        return NUFFT_ERR_ALLOC;
+    }
+    p.cap = cap;
+    return NUFFT_SUCCESS;
+}
+
+template <typename T> static int set_points_impl(Plan &p, int64_t np, const void *const x[])
+{
+    const TileGeom &g = p.geom;
+    BinGeom bg;
+    bg.D = p.D;
+    bg.convention = p.opts.point_convention;
+    for (int d = 0; d < 3; ++d) { bg.N[d] = g.N[d]; bg.B[d] = g.B[d]; bg.nb[d] = g.nb[d]; }
+    const T *x0 = (const T *)x[0];
+    const T *x1 = p.D > 1 ? (const T *)x[1] : nullptr;
+    const T *x2 = p.D > 2 ? (const T *)x[2] : nullptr;
+    cudaStream_t st = p.stream;
+
+    uint32_t *bin_count = (uint32_t *)p.d_bin_offsets;
+    CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
+    if (np > 0) {
+        const int grid = (int)std::min<int64_t>(cdiv(np, 256), 148 * 16);
+        bin_keys_kernel<T><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count);
+        NUFFT_COUNT_LAUNCH();
+    }
+    // slot b+1 holds the count of bin b and slot 0 stays 0: an inclusive scan of this array is exactly
+    // cumulative_npoints_per_block (reference layout, src/blocking/gpu.jl:12); done by the caller.
+    return NUFFT_SUCCESS;
+}
+
+template <typename T> static int run_set_points(Plan &p, int64_t np, const void *const x[])
+{
+    NUFFT_TRY(ensure_capacity(p, np));
+    NUFFT_TRY(set_points_impl<T>(p, np, x));
+    cudaStream_t st = p.stream;
+    const int64_t nb1 = p.nbins + 1;
+    NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_bin_offsets, nb1, true));
+
+    // stable LSD radix sort of (key, index)
+    const int passes = (p.nbins > 1 && np > 0) ? (p.key_bits + RADIX_BITS - 1) / RADIX_BITS : 0;
+    int cur = 0;
+    if (passes == 0) {
+        if (np > 0) {
+            iota_kernel<<<(unsigned)cdiv(np, 256), 256, 0, st>>>(p.d_vals[0], np);
+            NUFFT_COUNT_LAUNCH();
+        }
+        p.d_perm = p.d_vals[0];
+    } else {
+        const int nblk = (int)cdiv(np, SORT_TILE);
+        const size_t hneed = (size_t)nblk * RADIX;
+        if (hneed > p.hist_cap) {
+            if (p.d_hist) cudaFree(p.d_hist);
+            p.hist_cap = hneed + hneed / 8;
+            CUDA_TRY(cudaMalloc(&p.d_hist, p.hist_cap * sizeof(uint32_t)));
+        }
+        for (int pass = 0; pass < passes; ++pass) {
+            const int shift = pass * RADIX_BITS;
+            const bool first = pass == 0, last = pass == passes - 1;
+            radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], np, shift, p.d_hist, nblk);
+            NUFFT_COUNT_LAUNCH();
+            NUFFT_TRY(scan_u32(p, p.d_hist, (int64_t)hneed, false));
+            uint32_t *ko = p.d_keys[cur ^ 1];
+            int32_t *vo = p.d_vals[cur ^ 1];
+            if (first && last) radix_scatter_kernel<true, true><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
+            else if (first) radix_scatter_kernel<true, false><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
+            else if (last) radix_scatter_kernel<false, true><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
+            else radix_scatter_kernel<false, false><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
+            NUFFT_COUNT_LAUNCH();
+            cur ^= 1;
+        }
+        p.d_perm = p.d_vals[cur];
+    }
+    if (np > 0) {
+        gather_points_kernel<T><<<(unsigned)cdiv(np, 256), 256, 0, st>>>(
+            p.D, p.opts.point_convention, np, p.d_perm, (const T *)x[0], p.D > 1 ? (const T *)x[1] : nullptr,
+            p.D > 2 ? (const T *)x[2] : nullptr, (T *)p.d_xs[0], (T *)p.d_xs[1], (T *)p.d_xs[2]);
+        NUFFT_COUNT_LAUNCH();
+    }
+    // work items: bins with more than `chunk` points are split
+    work_items_kernel<<<(unsigned)cdiv(nb1, 256), 256, 0, st>>>(p.d_bin_offsets, p.nbins, p.geom.chunk, p.d_item_start);
+    NUFFT_COUNT_LAUNCH();
+    // inclusive scan of [0, n0, n1, ...]: item_start[b] = first item of bin b, item_start[nbins] = total
+    NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_item_start, nb1, true));
+    CUDA_TRY(cudaGetLastError());
+    return NUFFT_SUCCESS;
+}
+
+int binning_set_points(Plan &p, int64_t np, const void *const x[])
+{
+    if (np < 0) { set_error("negative number of points"); return NUFFT_ERR_ARG; }
+    if (np >= ((int64_t)1 << 31) - 4096) { set_error("number of points exceeds maximum allowed: 2^31"); return NUFFT_ERR_ARG; }
+    for (int d = 0; d < p.D; ++d) {
+        if (np > 0 && x[d] == nullptr) { set_error("null point array for dimension %d", d); return NUFFT_ERR_ARG; }
+        p.user_x[d] = x[d];
+    }
+    if (p.ev_ok) { cudaEventRecord(p.ev[0], p.stream); }
+    int rc = p.f64 ? run_set_points<double>(p, np, x) : run_set_points<float>(p, np, x);
+    if (rc != NUFFT_SUCCESS) return rc;
+    if (p.ev_ok) { cudaEventRecord(p.ev[1], p.stream); p.ev_rec[0] = true; }
+    p.Np = np;
+    return NUFFT_SUCCESS;
+}
+
+}  // namespace nufft

@@ -1,0 +1,223 @@
+// common.cuh — shared declarations of the B200 NUFFT backend (internal; the public ABI is include/nufft_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/nufft_b200.h"
+
+namespace nufft {
+
+constexpr int MAX_M = 12;          // largest half support instantiated
+constexpr int MIN_M = 2;
+constexpr int MAX_W = 2 * MAX_M;
+constexpr int MAX_NPOLY = MAX_M + 4;
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern thread_local int64_t g_launch_count;
+#define NUFFT_COUNT_LAUNCH() (++::nufft::g_launch_count)
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ::nufft::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                               cudaGetErrorString(_e));                                       \
+            return NUFFT_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define CUFFT_TRY(expr)                                                                       \
+    do {                                                                                      \
+        cufftResult _r = (expr);                                                              \
+        if (_r != CUFFT_SUCCESS) {                                                            \
+            ::nufft::set_error("cuFFT error %d at %s:%d", (int)_r, __FILE__, __LINE__);       \
+            return NUFFT_ERR_CUFFT;                                                           \
+        }                                                                                     \
+    } while (0)
+
+#define NUFFT_TRY(expr)            \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != NUFFT_SUCCESS) return _s; \
+    } while (0)
+
+// ---- cell (grid element) types --------------------------------------------------------------
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <typename T, bool CPLX> struct CellOf { using type = T; };
+template <typename T> struct CellOf<T, true> { using type = typename Vec2<T>::type; };
+
+template <typename T> __host__ __device__ inline T cell_zero(T *) { return T(0); }
+__host__ __device__ inline float2 cell_zero(float2 *) { return make_float2(0.f, 0.f); }
+__host__ __device__ inline double2 cell_zero(double2 *) { return make_double2(0., 0.); }
+
+// scale: cell * real
+__device__ __forceinline__ float cmul(float v, float s) { return v * s; }
+__device__ __forceinline__ double cmul(double v, double s) { return v * s; }
+__device__ __forceinline__ float2 cmul(float2 v, float s) { return make_float2(v.x * s, v.y * s); }
+__device__ __forceinline__ double2 cmul(double2 v, double s) { return make_double2(v.x * s, v.y * s); }
+// fused acc += v * s
+__device__ __forceinline__ void cfma(float &a, float v, float s) { a = fmaf(v, s, a); }
+__device__ __forceinline__ void cfma(double &a, double v, double s) { a = fma(v, s, a); }
+__device__ __forceinline__ void cfma(float2 &a, float2 v, float s) { a.x = fmaf(v.x, s, a.x); a.y = fmaf(v.y, s, a.y); }
+__device__ __forceinline__ void cfma(double2 &a, double2 v, double s) { a.x = fma(v.x, s, a.x); a.y = fma(v.y, s, a.y); }
+__device__ __forceinline__ bool cnonzero(float v) { return v != 0.f; }
+__device__ __forceinline__ bool cnonzero(double v) { return v != 0.; }
+__device__ __forceinline__ bool cnonzero(float2 v) { return v.x != 0.f || v.y != 0.f; }
+__device__ __forceinline__ bool cnonzero(double2 v) { return v.x != 0. || v.y != 0.; }
+
+// global atomic accumulate of one cell (complex f32 -> one REDG.F32x2 on sm_90+)
+__device__ __forceinline__ void catomic_add(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void catomic_add(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void catomic_add(float2 *p, float2 v) { atomicAdd(p, v); }
+__device__ __forceinline__ void catomic_add(double2 *p, double2 v)
+{
+    atomicAdd(&p->x, v.x);
+    atomicAdd(&p->y, v.y);
+}
+
+__device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ float2 shfl_xor(float2 v, int m)
+{
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ double2 shfl_xor(double2 v, int m)
+{
+    return make_double2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ float cadd(float a, float b) { return a + b; }
+__device__ __forceinline__ double cadd(double a, double b) { return a + b; }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+// ---- kernel (window function) parameters handed to device code by value ----------------------
+template <typename T> struct KernelParams {
+    int kind;        // NUFFT_KERNEL_*
+    int mode;        // NUFFT_EVAL_*
+    int M;
+    int N[3];        // oversampled grid size per dim
+    T beta[3];       // KB/BKB shape
+    T tau[3];        // Gaussian 2 sigma^2
+    T dx[3];         // 2pi / N
+    const T *cs;     // device: per dim d a block of CS_STRIDE values:
+                     //   [ (M+4)*2M polynomial coefs, layout [p][j] | M Gaussian exponentials ]
+    int cs_stride;   // = (M+4)*2M + M
+};
+
+// ---- geometry of bins / tiles handed to spreading & interpolation kernels ---------------------
+struct TileGeom {
+    int D;
+    int N[3];        // oversampled dims (1 for unused dims)
+    int B[3];        // bin dims
+    int nb[3];       // bins per dim
+    int T[3];        // tile dims = B + 2M - 1 (1 for unused dims)
+    int S[3];        // tile strides in cells: S[0]=1 implied; S[1]=row stride, S[2]=plane stride ; S[0] holds padded row length
+    int tile_cells;  // allocated cells per tile
+    int chunk;       // max points per work item
+    int batch;       // points per evaluation batch (shared-memory staging)
+};
+
+// ---- the plan ------------------------------------------------------------------------------------
+struct Plan {
+    nufft_opts opts{};
+    int D = 0, M = 0, C = 1;
+    bool cplx = false, f64 = false;
+    int method = NUFFT_METHOD_GLOBAL_MEMORY;   // resolved method
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t Ns[3] = {1, 1, 1};       // modes
+    int64_t Nos[3] = {1, 1, 1};      // oversampled physical dims
+    int64_t Nspec[3] = {1, 1, 1};    // oversampled spectral dims (r2c: first halved)
+    int64_t nk[3] = {1, 1, 1};       // size(plan)
+    int64_t ncells = 1, nspec = 1, nkept = 1;
+    size_t real_bytes = 4;
+
+    // host copies of kernel data (double) for introspection
+    double h_shape[3] = {0, 0, 0}, h_dx[3] = {0, 0, 0};
+    std::string h_cs[3];             // raw bytes of T cs block per dim
+    std::string h_phihat[3];         // raw bytes of T phihat per dim
+
+    // device tables
+    void *d_cs = nullptr;            // T[3*cs_stride]
+    int cs_stride = 0;
+    void *d_phihat[3] = {nullptr, nullptr, nullptr};   // T[nk[d]]
+    int32_t *d_imap[3] = {nullptr, nullptr, nullptr};  // kept index -> oversampled spectral index
+    int32_t *d_invmap[3] = {nullptr, nullptr, nullptr};// oversampled spectral index -> kept index or -1
+    double kp_beta[3] = {0, 0, 0}, kp_tau[3] = {0, 0, 0};
+
+    // grids
+    void *d_us = nullptr;            // C * ncells * sizeof(Z)
+    void *d_uhat = nullptr;          // real plans: C * nspec * sizeof(complex T); complex plans: alias of d_us
+    cufftHandle fft_fw = 0, fft_bw = 0;
+    bool fft_ok = false;
+    void *d_fft_work = nullptr;
+    size_t fft_work_bytes = 0;
+
+    // binning state
+    TileGeom geom{};
+    int64_t nbins = 1;
+    int key_bits = 1;
+    int64_t Np = -1;
+    int64_t cap = 0;                 // capacity (points) of the buffers below
+    const void *user_x[3] = {nullptr, nullptr, nullptr};
+    uint32_t *d_keys[2] = {nullptr, nullptr};
+    int32_t *d_vals[2] = {nullptr, nullptr};
+    int32_t *d_perm = nullptr;       // alias into d_vals
+    void *d_xs[3] = {nullptr, nullptr, nullptr};       // sorted, folded coordinates (T)
+    int32_t *d_bin_offsets = nullptr;                  // nbins + 1
+    uint32_t *d_hist = nullptr;      // radix histograms
+    size_t hist_cap = 0;
+    uint32_t *d_scan_tmp = nullptr;
+    size_t scan_tmp_cap = 0;
+    int32_t *d_item_start = nullptr; // nbins + 1: exclusive scan of work items per bin
+    int32_t *d_counters = nullptr;   // small block of device counters
+
+    // timings
+    cudaEvent_t ev[32] = {};
+    bool ev_ok = false;
+    bool ev_rec[32] = {};
+    float ms[16] = {};
+
+    bool sticky_error = false;
+};
+
+// kernel-launch helper: ceil-div
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- stage implementations (one .cu each) ---------------------------------------------------
+int host_plan_init(Plan &p);                 // host_plan.cu: sizes, kernel data, tables, geometry, FFT plans
+void host_plan_free(Plan &p);
+int binning_set_points(Plan &p, int64_t np, const void *const x[]);        // binning.cu
+int spread_run(Plan &p, const void *const vp[], const nufft_callbacks *cb); // spread_*.cu
+int interp_run(Plan &p, void *const vp[], const nufft_callbacks *cb);       // interp_*.cu
+int deconv_type1_run(Plan &p, void *const uhat[], const nufft_callbacks *cb); // deconv.cu
+int deconv_type2_run(Plan &p, const void *const uhat[], const nufft_callbacks *cb);
+int fft_forward(Plan &p);
+int fft_backward(Plan &p);
+int scan_u32(Plan &p, uint32_t *data, int64_t n, bool inclusive);          // binning.cu (in place prefix sum)
+
+template <typename T> KernelParams<T> make_kernel_params(const Plan &p)
+{
+    KernelParams<T> kp;
+    kp.kind = p.opts.kernel;
+    kp.mode = p.opts.eval_mode;
+    kp.M = p.M;
+    for (int d = 0; d < 3; ++d) {
+        kp.N[d] = (int)p.Nos[d];
+        kp.beta[d] = (T)p.kp_beta[d];
+        kp.tau[d] = (T)p.kp_tau[d];
+        kp.dx[d] = (T)2 * (T)3.14159265358979323846 / (T)p.Nos[d];
+    }
+    kp.cs = (const T *)p.d_cs;
+    kp.cs_stride = p.cs_stride;
+    return kp;
+}
+
+}  // namespace nufft

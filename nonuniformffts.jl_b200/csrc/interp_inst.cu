@@ -1,0 +1,80 @@
+// interp_inst.cu — instantiates the K-interp kernels for one (T, CPLX) pair.
+// Compiled four times: -DINST_T=float|double -DINST_CPLX=0|1.
+#include <algorithm>
+#include "interp.cuh"
+
+#ifndef INST_T
+#define INST_T float
+#endif
+#ifndef INST_CPLX
+#define INST_CPLX 1
+#endif
+
+namespace nufft {
+
+template <typename T, bool CPLX, int D, int M>
+static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
+{
+    using Cell = typename CellOf<T, CPLX>::type;
+    cudaStream_t st = p.stream;
+    const int64_t np = p.Np;
+    if (np == 0) return NUFFT_SUCCESS;
+    const KernelParams<T> kp = make_kernel_params<T>(p);
+    const T *nuw = (cb && cb->nu_weights) ? (const T *)cb->nu_weights : nullptr;
+    const T *xs0 = (const T *)p.d_xs[0], *xs1 = (const T *)p.d_xs[1], *xs2 = (const T *)p.d_xs[2];
+    T prefactor = (T)1;
+    for (int d = 0; d < D; ++d) prefactor *= kp.dx[d];
+    for (int c0 = 0; c0 < p.C; c0 += MAX_PACK) {
+        const int cn = std::min(MAX_PACK, p.C - c0);
+        MutPtrPack pack{};
+        for (int c = 0; c < cn; ++c) pack.p[c] = vp[c0 + c];
+        const Cell *us = (const Cell *)p.d_us + (int64_t)c0 * p.ncells;
+        if (p.method == NUFFT_METHOD_GLOBAL_MEMORY) {
+            interp_gm_kernel<T, CPLX, D, M><<<(unsigned)cdiv(np, 128), 128, 0, st>>>(
+                kp, np, xs0, xs1, xs2, p.d_perm, pack, cn, us, p.ncells, prefactor, nuw);
+            NUFFT_COUNT_LAUNCH();
+        } else {
+            auto kern = interp_sm_kernel<T, CPLX, D, M>;
+            const size_t smem = sm_dynamic_bytes<T, CPLX, D, M>(p.geom, p.cs_stride);
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int occ = 0, nsm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, INTERP_THREADS, smem));
+            CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+            if (occ < 1) { set_error("interp_sm_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
+            SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_counters, (int)p.nbins};
+            CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
+            kern<<<nsm * occ, INTERP_THREADS, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, prefactor, nuw);
+            NUFFT_COUNT_LAUNCH();
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return NUFFT_SUCCESS;
+}
+
+#define NUFFT_M_CASES(D_) \
+    case 2: return interp_launch<T, CPLX, D_, 2>(p, vp, cb);   \
+    case 3: return interp_launch<T, CPLX, D_, 3>(p, vp, cb);   \
+    case 4: return interp_launch<T, CPLX, D_, 4>(p, vp, cb);   \
+    case 5: return interp_launch<T, CPLX, D_, 5>(p, vp, cb);   \
+    case 6: return interp_launch<T, CPLX, D_, 6>(p, vp, cb);   \
+    case 7: return interp_launch<T, CPLX, D_, 7>(p, vp, cb);   \
+    case 8: return interp_launch<T, CPLX, D_, 8>(p, vp, cb);   \
+    case 9: return interp_launch<T, CPLX, D_, 9>(p, vp, cb);   \
+    case 10: return interp_launch<T, CPLX, D_, 10>(p, vp, cb); \
+    case 11: return interp_launch<T, CPLX, D_, 11>(p, vp, cb); \
+    case 12: return interp_launch<T, CPLX, D_, 12>(p, vp, cb);
+
+template <typename T, bool CPLX> int interp_dispatch(Plan &p, void *const vp[], const nufft_callbacks *cb)
+{
+    switch (p.D) {
+    case 1: switch (p.M) { NUFFT_M_CASES(1) } break;
+    case 2: switch (p.M) { NUFFT_M_CASES(2) } break;
+    case 3: switch (p.M) { NUFFT_M_CASES(3) } break;
+    }
+    set_error("interpolation kernel not instantiated for D = %d, M = %d", p.D, p.M);
+    return NUFFT_ERR_UNSUPPORTED;
+}
+
+template int interp_dispatch<INST_T, (INST_CPLX != 0)>(Plan &, void *const[], const nufft_callbacks *);
+
+}  // namespace nufft
