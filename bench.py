@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""
+bench.py — headline benchmark of the B200-native NUFFT backend (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): 3-D NUFFT type-1/type-2 points/s at 256^3 modes, Np = 256^3 (config C3:
+ComplexF32, HalfSupport(4), default sigma = 2 -> 512^3 oversampled grid, uniform-random points).
+A "step" follows the reference's protocol (benchmark/CPU+CUDA/run_benchmarks.jl:82-92) for both
+transform types back to back:   set_points! + exec_type1!   then   set_points! + exec_type2!
+so one step processes 2*Np points per GPU.  `value` = points / s with inputs resident in HBM;
+`e2e` = the same through the public API with pinned HOST buffers (H2D of points+values / spectrum and
+D2H of the result inside the timed region).
+
+N > 1 (torchrun, one rank per GPU): weak scaling of the point-partitioned transform — every rank holds
+its own 2^24 points of ONE 256^3 problem; type-1 partial results are summed with an NCCL all-reduce,
+type-2 broadcasts the spectrum and splits the points.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port, all host threads) on a
+bounded sample of the same workload.  The oracle is only ever used there and in `cpu_baseline`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_MODES = 256
+NP_FULL = 256 ** 3
+HALF_SUPPORT = 4
+SIGMA = 2.0
+KERNEL = "backwards_kaiser_bessel"      # + FastApproximation == the reference CPU path's defaults
+METRIC = "3D NUFFT type-1/type-2 points/sec at 256^3 modes, Np=256^3, vs HBM roofline"
+UNIT = "points/s"
+
+
+def measured_peak_gbs():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(seed: int, npts: int):
+    rng = np.random.default_rng(seed)
+    xs = [(rng.random(npts, dtype=np.float32) * np.float32(2 * np.pi)) for _ in range(3)]
+    two_pi = np.float32(2) * np.float32(np.pi)
+    for x in xs:
+        x[x >= two_pi] = 0.0
+    vp = (rng.standard_normal(npts, dtype=np.float32) + 1j * rng.standard_normal(npts, dtype=np.float32)).astype(np.complex64)
+    nk = N_MODES ** 3
+    uk = (rng.standard_normal(nk, dtype=np.float32) + 1j * rng.standard_normal(nk, dtype=np.float32)).astype(np.complex64)
+    return xs, vp, uk.reshape(N_MODES, N_MODES, N_MODES)
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(steps: int, warmup: int, sample_points: int):
+    import oracle
+    cores = oracle.num_threads()
+    xs, vp, uk = make_inputs(3, sample_points)
+    plan = oracle.OraclePlan(np.complex64, (N_MODES,) * 3, m=HALF_SUPPORT, sigma=SIGMA, kernel=KERNEL, evalmode="fast",
+                             block_size=4096, use_blocked_spreading=True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        plan.set_points(xs)
+        plan.exec_type1(vp)
+        plan.set_points(xs)
+        plan.exec_type2(uk)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    value = 2.0 * sample_points * len(times) / total
+    return value, cores, total / len(times) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample = NP_FULL
+    steps = max(1, min(args.steps, 3))          # each full-size CPU step takes ~10-20 s: bound the run to a few minutes
+    warm = 1 if args.warmup > 0 else 0
+    value, cores, ms = cpu_reference_run(steps, warm, sample)
+    sample_desc = (f"full C3 workload per step (256^3 modes, 512^3 oversampled grid, Np = 2^24 uniform-random points), "
+                   f"{steps} timed step(s) after {warm} warm-up (step count bounded to keep the run within minutes); "
+                   "restatement of the reference CPU algorithm (oracle port: blocked spreading/interpolation + OpenMP, "
+                   "pocketfft), NOT NonuniformFFTs.jl itself (no Julia in this image)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: 3D 256^3 modes, ComplexF32, HalfSupport(4), sigma=2, uniform-random points "
+                               "Np=2^24; step = set_points+type1, set_points+type2 (2*Np points per step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import nufft_b200 as nb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    npts = NP_FULL
+    K, W = args.steps, max(args.warmup, 3)
+
+    xs_h, vp_h, uk_h = make_inputs(3 + rank, npts)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    xs_pin, vp_pin, uk_pin = [pin(x) for x in xs_h], pin(vp_h), pin(uk_h)
+    xs_d = [x.to(dev) for x in xs_pin]
+    vp_d, uk_d = vp_pin.to(dev), uk_pin.to(dev)
+    out1_d = torch.empty((N_MODES,) * 3, dtype=torch.complex64, device=dev)
+    out2_d = torch.empty(npts, dtype=torch.complex64, device=dev)
+    out1_pin = torch.empty((N_MODES,) * 3, dtype=torch.complex64).pin_memory()
+    out2_pin = torch.empty(npts, dtype=torch.complex64).pin_memory()
+
+    plan = nb.PlanNUFFT(torch.complex64, (N_MODES,) * 3, m=HALF_SUPPORT, sigma=SIGMA,
+                        kernel=nb.BackwardsKaiserBesselKernel(), kernel_evalmode=nb.FastApproximation(),
+                        timer=True, device=dev)
+
+    def step_device():
+        plan.set_points(tuple(xs_d))
+        plan.exec_type1(out1_d, vp_d)
+        if world > 1:
+            dist.all_reduce(out1_d)                      # sum of the per-rank partial type-1 results (NVLink)
+        plan.set_points(tuple(xs_d))
+        if world > 1:
+            dist.broadcast(uk_d, src=0)                  # type-2: spectrum broadcast, points split
+        plan.exec_type2(out2_d, uk_d)
+
+    def step_e2e():
+        xd = [x.to(dev, non_blocking=True) for x in xs_pin]
+        vd = vp_pin.to(dev, non_blocking=True)
+        plan.set_points(tuple(xd))
+        plan.exec_type1(out1_d, vd)
+        if world > 1:
+            dist.all_reduce(out1_d)
+        out1_pin.copy_(out1_d, non_blocking=True)
+        ud = uk_pin.to(dev, non_blocking=True)
+        plan.set_points(tuple(xd))
+        if world > 1:
+            dist.broadcast(ud, src=0)
+        plan.exec_type2(out2_d, ud)
+        out2_pin.copy_(out2_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller reads the host results
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(W):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    nb.launch_count(reset=True)
+    ms_total = timed(step_device, K)
+    launches = nb.launch_count(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+    timer = plan.timer                                    # per-stage device times of the last step
+    # per-type timings (separate loops, same protocol)
+    def t1_only():
+        plan.set_points(tuple(xs_d)); plan.exec_type1(out1_d, vp_d)
+    def t2_only():
+        plan.set_points(tuple(xs_d)); plan.exec_type2(out2_d, uk_d)
+    ms_t1 = timed(t1_only, K) / K
+    ms_t2 = timed(t2_only, K) / K
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, K)
+
+    pts_per_step = 2.0 * npts * world
+    value = pts_per_step * K / (ms_total * 1e-3)
+    e2e_value = pts_per_step * K / (ms_e2e * 1e-3)
+    h2d = sum(x.numel() * 4 for x in xs_pin) + vp_pin.numel() * 8 + uk_pin.numel() * 8
+    d2h = out1_pin.numel() * 8 + out2_pin.numel() * 8
+
+    # roofline of the dominant kernel (K-spread): algorithmic bytes = Np*(D*s_T + C*s_Z + 4) + C*G_x
+    peak, peak_src = measured_peak_gbs()
+    G_x = (2 * N_MODES) ** 3 * 8
+    stages = {"spread": (timer["T1 (1) Spreading"], npts * (3 * 4 + 8 + 4) + G_x),
+              "interp": (timer["T2 (3) Interpolation"], G_x + npts * (3 * 4 + 4 + 8))}
+    dom = max(stages, key=lambda k: stages[k][0])
+    dom_ms, dom_bytes = stages[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # whole-transform fractions (B_1 + B_sp, B_2 + B_sp of SURVEY §8d)
+    B_sp = npts * 16
+    B_1 = npts * 24 + 3 * G_x + 2 * N_MODES ** 3 * 8
+    B_2 = N_MODES ** 3 * 8 + 4 * G_x + npts * 24
+    roof = {"bound": "hbm", "kernel": f"K-{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "launch_ms": dom_ms,
+            "type1_incl_set_points_frac": (B_1 + B_sp) / (ms_t1 * 1e-3) / 1e9 / peak,
+            "type2_incl_set_points_frac": (B_2 + B_sp) / (ms_t2 * 1e-3) / 1e9 / peak,
+            "stage_ms": timer}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, ms = cpu_reference_run(1, 0, NP_FULL)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+                   "sample": "ONE full-size step (set_points+type1, set_points+type2; 256^3 modes, 512^3 oversampled grid, "
+                             "Np = 2^24), no warm-up; oracle port of the reference CPU algorithm (blocked, OpenMP + pocketfft)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3: 3D 256^3 modes, Np=2^24 uniform-random points per GPU, ComplexF32, HalfSupport(4), "
+                                   "sigma=2 (512^3 grid), BackwardsKaiserBessel+FastApproximation; step = set_points+type1, "
+                                   "set_points+type2 (2*Np points per GPU per step)",
+                       "l2": "inputs larger than L2 (1 GiB grid + 320 MiB points/values per transform)",
+                       "multi_gpu": "points partitioned; type-1 partial outputs all-reduced (NCCL), type-2 spectrum broadcast"
+                       if world > 1 else "single GPU"},
+            "type1_points_per_s": npts * world / (ms_t1 * 1e-3), "type2_points_per_s": npts * world / (ms_t2 * 1e-3),
+            "type1_ms": ms_t1, "type2_ms": ms_t2,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -205,15 +205,40 @@ size_t sm_batch_bytes(int D, int M, size_t real_bytes, size_t cell_bytes, int ba
     return (size_t)batch * ((size_t)D * 2 * M * real_bytes + 16 + cell_bytes);
 }
 
-static int padded_row(int Tx, int W)
+// Shared-memory wavefronts needed by one warp-wide tile access of the spreading / interpolation kernels:
+// lane -> (lx = lane % W, lg = lane / W), cell = base + lg * Sx + lx; lanes >= (32 / W) * W idle.
+// 4-byte cells are served 32 lanes per wavefront, 8-byte cells 16 lanes, 16-byte cells 8 lanes.
+static int tile_access_wavefronts(int Sx, int W, int cell_bytes)
 {
-    // row stride in cells: keep rows of consecutive y in different banks (see DESIGN.md, K-spread)
-    if (W == 8 || W == 16 || W == 4) {
-        int s = Tx;
-        while (s % (2 * W) != W) ++s;
-        return s;
+    const int G = 32 / W, lanes_per_phase = 128 / cell_bytes, groups = 128 / cell_bytes;
+    int worst = 0;
+    for (int base = 0; base < groups; ++base) {
+        int total = 0;
+        for (int ph = 0; ph * lanes_per_phase < 32; ++ph) {
+            int cnt[32] = {0};
+            int mx = 0;
+            for (int l = ph * lanes_per_phase; l < (ph + 1) * lanes_per_phase; ++l) {
+                const int lx = l % W, lg = l / W;
+                if (lg >= G) continue;
+                const int c = (base + lg * Sx + lx) % groups;
+                mx = std::max(mx, ++cnt[c]);
+            }
+            total += mx;
+        }
+        worst = std::max(worst, total);
     }
-    return Tx | 1;
+    return worst;
+}
+
+// row stride (cells) of the shared-memory tile: smallest padding that minimises bank conflicts
+static int padded_row(int Tx, int W, int cell_bytes)
+{
+    int best = Tx, best_wf = 1 << 30;
+    for (int s = Tx; s <= Tx + 32 && s <= Tx + Tx / 4 + 1; ++s) {
+        const int wf = tile_access_wavefronts(s, W, cell_bytes);
+        if (wf < best_wf) { best_wf = wf; best = s; }
+    }
+    return best;
 }
 
 static bool choose_geometry(Plan &p)
@@ -228,7 +253,7 @@ static bool choose_geometry(Plan &p)
 
     auto tile_bytes = [&](const int *B, int *T, int *S) -> size_t {
         for (int d = 0; d < 3; ++d) T[d] = (d < D) ? B[d] + W - 1 : 1;
-        S[0] = padded_row(T[0], W);
+        S[0] = padded_row(T[0], W, (int)cell_bytes);
         S[1] = S[0];
         S[2] = S[0] * T[1];
         return (size_t)S[0] * T[1] * T[2] * cell_bytes;

@@ -372,10 +372,18 @@ class OraclePlan:
         vps = [np.empty(self.Np, dtype=self.Z) for _ in range(self.C)]
         w = None if nu_weights is None else np.ascontiguousarray(nu_weights, dtype=self.T)
         ncomp = 2 if self.is_complex else 1
-        getattr(lib(), "orc_interp" + self.suf)(
-            C.c_int(self.D), self._i64(self.Nos), self._kptr(0), C.c_int(self.mode), C.c_int64(self.Np),
-            self._ptrs(self.points), C.c_int(self.convention), C.c_int(self.C), C.c_int(ncomp),
-            self._ptrs(vps), self._ptrs(us), None if w is None else w.ctypes.data_as(C.c_void_p))
+        wp = None if w is None else w.ctypes.data_as(C.c_void_p)
+        if self.use_blocked and self.block_dims is not None:
+            getattr(lib(), "orc_interp_blocked" + self.suf)(
+                C.c_int(self.D), self._i64(self.Nos), self._kptr(0), C.c_int(self.mode), C.c_int64(self.Np),
+                self._ptrs(self.points), C.c_int(self.convention), C.c_int(self.C), C.c_int(ncomp),
+                self._ptrs(vps), self._ptrs(us), wp, self._i64(self.block_dims),
+                self.cum.ctypes.data_as(C.c_void_p), self.perm.ctypes.data_as(C.c_void_p))
+        else:
+            getattr(lib(), "orc_interp" + self.suf)(
+                C.c_int(self.D), self._i64(self.Nos), self._kptr(0), C.c_int(self.mode), C.c_int64(self.Np),
+                self._ptrs(self.points), C.c_int(self.convention), C.c_int(self.C), C.c_int(ncomp),
+                self._ptrs(vps), self._ptrs(us), wp)
         return vps
 
     def exec_type2(self, uks, nu_weights=None, u_factor=None):

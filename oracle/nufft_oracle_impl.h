@@ -416,11 +416,31 @@ void SUF(orc_spread_blocked)(int D, const int64_t *Ns, const SUF(orc_kernel) *gs
     }
     const int64_t bufcells = pad[0] * pad[1] * pad[2];
     (void)Np;
+    /* Merge strategy: the reference merges block buffers under a lock (:156-163) or with atomics (:201-214).
+     * Here blocks are processed in "colours": two blocks whose coordinates differ by >= ncol[d] blocks in some
+     * dimension have disjoint padded regions, so blocks of one colour are merged concurrently with plain adds
+     * (same sums; no lock contention, no CAS loops).  ncol[d] = number of blocks a padded buffer can overlap. */
+    int64_t ncol[3] = {1, 1, 1};
+    for (int d = 0; d < D; ++d) {
+        const int64_t need = (pad[d] + B[d] - 1) / B[d] + 1;   /* +1: the last block may stick out past N */
+        ncol[d] = need;
+        if (ncol[d] > nb[d]) ncol[d] = nb[d];
+        /* periodic wrap: colours must also separate the first and last blocks */
+        while (ncol[d] < nb[d] && (nb[d] % ncol[d]) != 0 && (nb[d] % ncol[d]) < need) ++ncol[d];
+    }
+    const int64_t ncolors = ncol[0] * ncol[1] * ncol[2];
 #pragma omp parallel
     {
         REAL *buf = (REAL *)malloc(sizeof(REAL) * (size_t)(bufcells * ncomp));
+        for (int64_t color = 0; color < ncolors; ++color) {
+            const int64_t c0 = color % ncol[0], c1 = (color / ncol[0]) % ncol[1], c2 = color / (ncol[0] * ncol[1]);
+            const int64_t m0 = (nb[0] - c0 + ncol[0] - 1) / ncol[0], m1 = (nb[1] - c1 + ncol[1] - 1) / ncol[1],
+                          m2 = (nb[2] - c2 + ncol[2] - 1) / ncol[2];
+            const int64_t nblk_color = m0 * m1 * m2;
 #pragma omp for schedule(dynamic, 1)
-        for (int64_t j = 0; j < nblocks; ++j) {
+        for (int64_t jj = 0; jj < nblk_color; ++jj) {
+            const int64_t b0 = c0 + (jj % m0) * ncol[0], b1 = c1 + ((jj / m0) % m1) * ncol[1], b2 = c2 + (jj / (m0 * m1)) * ncol[2];
+            const int64_t j = (b2 * nb[1] + b1) * nb[0] + b0;
             const int32_t a = cum[j], b = cum[j + 1];
             if (a == b) continue;
             int64_t I0[3];                           /* 0-based first cell of the block */
@@ -434,8 +454,7 @@ void SUF(orc_spread_blocked)(int D, const int64_t *Ns, const SUF(orc_kernel) *gs
                     for (int d = 0; d < D; ++d) {
                         REAL y = SUF(orc_transform_fold)(xs[d][l], convention);
                         int64_t i = SUF(orc_kernel_eval)(&gs[d], mode, y, vals[d]);   /* 1-based */
-                        /* local 0-based start: (i - M + 1) + (M - I0_1based...) cpu_blocked.jl:49-56 */
-                        st[d] = (i - 1) - I0[d] + 1;   /* buffer index 0 is unused, as in the reference */
+                        st[d] = (i - 1) - I0[d] + 1;   /* cpu_blocked.jl:49-56; buffer index 0 is unused, as in the reference */
                         wd[d] = W;
                     }
                     REAL vr = vp[c][ncomp * l], vi = (ncomp == 2) ? vp[c][2 * l + 1] : 0;
@@ -462,19 +481,15 @@ void SUF(orc_spread_blocked)(int D, const int64_t *Ns, const SUF(orc_kernel) *gs
                         int64_t gy = (D > 1) ? ((I0[1] - M + qy) % Nd[1] + Nd[1]) % Nd[1] : 0;
                         const REAL *src = buf + ncomp * ((qz * pad[1] + qy) * pad[0]);
                         REAL *dst = u + ncomp * ((gz * Nd[1] + gy) * Nd[0]);
+                        int64_t gx = ((I0[0] - M) % Nd[0] + Nd[0]) % Nd[0];
                         for (int64_t qx = 0; qx < pad[0]; ++qx) {
-                            int64_t gx = ((I0[0] - M + qx) % Nd[0] + Nd[0]) % Nd[0];
-                            for (int e = 0; e < ncomp; ++e) {
-                                REAL wv = src[ncomp * qx + e];
-                                if (wv != 0) {
-#pragma omp atomic
-                                    dst[ncomp * gx + e] += wv;
-                                }
-                            }
+                            for (int e = 0; e < ncomp; ++e) dst[ncomp * gx + e] += src[ncomp * qx + e];
+                            if (++gx == Nd[0]) gx = 0;
                         }
                     }
                 }
             }
+        }   /* omp for: implicit barrier between colours */
         }
         free(buf);
     }
@@ -523,6 +538,88 @@ void SUF(orc_interp)(int D, const int64_t *Ns, const SUF(orc_kernel) *gs, int mo
             if (ncomp == 2) { vp[c][2 * n] = ar; vp[c][2 * n + 1] = ai; }
             else vp[c][n] = ar;
         }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Type-2 interpolation, blocked + threaded form (the reference's default CPU path; timed CPU baseline):
+ * src/interpolation/cpu_blocked.jl:95-153 (driver over blocks), :156-206 (copy_to_block!),
+ * :1-35 (interpolate_blocked; values scaled by dx :29-32), :38-93 (dot products).
+ * ------------------------------------------------------------------------------------------ */
+void SUF(orc_interp_blocked)(int D, const int64_t *Ns, const SUF(orc_kernel) *gs, int mode,
+                             int64_t Np, const REAL *const *xs, int convention,
+                             int C, int ncomp, REAL *const *vp, const REAL *const *us,
+                             const REAL *nu_weights,
+                             const int64_t *block_dims, const int32_t *cum, const int32_t *perm)
+{
+    const int M = gs[0].M, W = 2 * M;
+    int64_t nb[3] = {1, 1, 1}, B[3] = {1, 1, 1}, Nd[3] = {1, 1, 1}, pad[3] = {1, 1, 1}, nblocks = 1;
+    for (int d = 0; d < D; ++d) {
+        B[d] = block_dims[d]; Nd[d] = Ns[d];
+        nb[d] = (Ns[d] + B[d] - 1) / B[d]; nblocks *= nb[d];
+        pad[d] = B[d] + 2 * M;
+    }
+    const int64_t bufcells = pad[0] * pad[1] * pad[2];
+    (void)Np;
+#pragma omp parallel
+    {
+        REAL *buf = (REAL *)malloc(sizeof(REAL) * (size_t)(bufcells * ncomp));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t j = 0; j < nblocks; ++j) {
+            const int32_t a = cum[j], b = cum[j + 1];
+            if (a == b) continue;
+            int64_t I0[3];
+            { int64_t t = j; for (int d = 0; d < 3; ++d) { I0[d] = (t % nb[d]) * B[d]; t /= nb[d]; } }
+            for (int c = 0; c < C; ++c) {
+                const REAL *u = us[c];
+                for (int64_t qz = 0; qz < pad[2]; ++qz) {
+                    int64_t gz = (D > 2) ? ((I0[2] - M + qz) % Nd[2] + Nd[2]) % Nd[2] : 0;
+                    for (int64_t qy = 0; qy < pad[1]; ++qy) {
+                        int64_t gy = (D > 1) ? ((I0[1] - M + qy) % Nd[1] + Nd[1]) % Nd[1] : 0;
+                        REAL *dst = buf + ncomp * ((qz * pad[1] + qy) * pad[0]);
+                        const REAL *src = u + ncomp * ((gz * Nd[1] + gy) * Nd[0]);
+                        int64_t gx = ((I0[0] - M) % Nd[0] + Nd[0]) % Nd[0];
+                        for (int64_t qx = 0; qx < pad[0]; ++qx) {
+                            for (int e = 0; e < ncomp; ++e) dst[ncomp * qx + e] = src[ncomp * gx + e];
+                            if (++gx == Nd[0]) gx = 0;
+                        }
+                    }
+                }
+                for (int32_t k = a; k < b; ++k) {
+                    const int64_t l = perm[k];
+                    REAL vals[3][ORC_MAXW]; int64_t st[3] = {0, 0, 0}; int wd[3] = {1, 1, 1};
+                    vals[1][0] = 1; vals[2][0] = 1;
+                    for (int d = 0; d < D; ++d) {
+                        REAL y = SUF(orc_transform_fold)(xs[d][l], convention);
+                        int64_t i = SUF(orc_kernel_eval)(&gs[d], mode, y, vals[d]);
+                        for (int q = 0; q < W; ++q) vals[d][q] *= gs[d].dx;
+                        st[d] = (i - 1) - I0[d] + 1;
+                        wd[d] = W;
+                    }
+                    REAL ar = 0, ai = 0;
+                    for (int jz = 0; jz < wd[2]; ++jz)
+                        for (int jy = 0; jy < wd[1]; ++jy) {
+                            REAL gt = (D == 1) ? (REAL)1 : (D == 2 ? vals[1][jy] : vals[2][jz] * vals[1][jy]);
+                            int64_t o = ((st[2] + jz) * pad[1] + (st[1] + jy)) * pad[0] + st[0];
+                            if (ncomp == 2) {
+                                const REAL *p = buf + 2 * o;
+                                REAL sr = 0, si = 0;
+                                for (int jx = 0; jx < W; ++jx) { sr += vals[0][jx] * p[2 * jx]; si += vals[0][jx] * p[2 * jx + 1]; }
+                                ar += gt * sr; ai += gt * si;
+                            } else {
+                                const REAL *p = buf + o;
+                                REAL sr = 0;
+                                for (int jx = 0; jx < W; ++jx) sr += vals[0][jx] * p[jx];
+                                ar += gt * sr;
+                            }
+                        }
+                    if (nu_weights) { ar *= nu_weights[l]; ai *= nu_weights[l]; }
+                    if (ncomp == 2) { vp[c][2 * l] = ar; vp[c][2 * l + 1] = ai; }
+                    else vp[c][l] = ar;
+                }
+            }
+        }
+        free(buf);
     }
 }
 

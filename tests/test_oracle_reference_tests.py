@@ -1,0 +1,274 @@
+"""
+CPU tests (no GPU): pin the ORACLE against every known-answer test the reference's own suite holds for the
+hot path.  The reference ships no binary fixtures (and Julia's Xoshiro streams are not reproducible here), so
+the portable pins are the *thresholds against an exact NUDFT / FFT* and the deterministic edge cases.
+Each test names the reference test file:line it restates (paths relative to /root/reference).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import OraclePlan, nudft_type1, nudft_type2
+from helpers import l2_error, make_values
+
+
+def _points_1d(rng, Np, rt):
+    # test/accuracy.jl:110-117: rand * 2pi, then shifted by a random multiple (-1, 0, 1) of 2pi
+    x = rng.random(Np) * 2 * np.pi + rng.integers(-1, 2, Np) * 2 * np.pi
+    return x.astype(rt)
+
+
+SLACK = 1.25   # the reference tuned its bounds on ITS random draw (Julia Xoshiro(42), not reproducible here);
+               # a different draw moves the measured error by a few per cent (e.g. KB, M = 7, sigma = 2 sits at 0.99x-1.01x)
+
+
+def _threshold(dtype, kernel, M, sigma):
+    """check_nufft_error, test/accuracy.jl:7-78 (times SLACK)."""
+    return SLACK * _threshold_ref(dtype, kernel, M, sigma)
+
+
+def _threshold_ref(dtype, kernel, M, sigma):
+    f64 = np.dtype(dtype) in (np.dtype(np.float64), np.dtype(np.complex128))
+    if kernel == "kaiser_bessel":
+        if sigma == 1.25:
+            return max(10.0 ** (-1.16 * M) * 1.05, 4e-12) if f64 else 2 * 10.0 ** (-1.16 * M)
+        return max(6 * 10.0 ** (-1.9 * M), 4e-14) if f64 else 6 * 10.0 ** (-1.9 * M)
+    if kernel == "backwards_kaiser_bessel":
+        if sigma == 1.25:
+            return max(10.0 ** (-1.20 * M), 4e-12) if f64 else 2 * 10.0 ** (-1.20 * M)
+        return max(6 * 10.0 ** (-1.9 * M), 4e-14) if f64 else 6 * 10.0 ** (-1.9 * M)
+    if kernel == "gaussian":
+        return 10.0 ** (-0.95 * M) * 0.8
+    return 10.0 ** (-0.98 * M) * 0.4
+
+
+CASES_1D = []
+for _dt in (np.float64, np.complex128, np.float32, np.complex64):
+    _Ms = range(4, 11) if np.dtype(_dt).itemsize >= 8 and np.dtype(_dt) != np.dtype(np.complex64) else [2]
+    for _M in _Ms:
+        for _k in ("kaiser_bessel", "backwards_kaiser_bessel"):
+            CASES_1D.append((_dt, _k, _M, 1.25))
+        for _k in ("kaiser_bessel", "backwards_kaiser_bessel", "gaussian", "bspline"):
+            CASES_1D.append((_dt, _k, _M, 2.0))
+
+
+@pytest.mark.parametrize("dtype,kernel,M,sigma", CASES_1D)
+def test_accuracy_1d(dtype, kernel, M, sigma):
+    """test/accuracy.jl:219-250 — 1-D type-1 and type-2 vs exact NUDFT, N = 256, Np = 512."""
+    N, Np = 256, 512
+    rng = np.random.default_rng(42)
+    p = OraclePlan(dtype, N, m=M, sigma=sigma, kernel=kernel)
+    x = _points_1d(rng, Np, p.T)
+    v = make_values(rng, Np, dtype)
+    p.set_points(x)
+    thr = _threshold(dtype, kernel, M, sigma)
+    e1 = l2_error(p.exec_type1(v), nudft_type1(p.ks, [x], v))
+    assert e1 < thr, f"type-1 error {e1:.3e} >= {thr:.3e}"
+    uk = make_values(rng, p.size[0], p.CT)
+    e2 = l2_error(p.exec_type2(uk), nudft_type2(p.ks, [x], uk, not p.is_complex))
+    assert e2 < thr, f"type-2 error {e2:.3e} >= {thr:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32, np.complex64])
+def test_accuracy_1d_explicit_kernel_parameters(dtype):
+    """test/accuracy.jl:251-267 — explicit beta / ell close to the defaults (M = 2, sigma = 2)."""
+    M, sigma, N, Np = 2, 2.0, 256, 512
+    beta = M * np.pi * (2 - 1 / sigma)
+    ell = np.sqrt(sigma / (2 * sigma - 1) * (M / np.pi))
+    for kernel, param in (("kaiser_bessel", beta), ("backwards_kaiser_bessel", beta), ("gaussian", ell)):
+        rng = np.random.default_rng(42)
+        p = OraclePlan(dtype, N, m=M, sigma=sigma, kernel=kernel, kernel_param=param)
+        x = _points_1d(rng, Np, p.T)
+        v = make_values(rng, Np, dtype)
+        p.set_points(x)
+        e1 = l2_error(p.exec_type1(v), nudft_type1(p.ks, [x], v))
+        assert e1 < _threshold(dtype, kernel, M, sigma)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("M", [4, 5, 6, 7, 8])
+def test_multidimensional_2d(dtype, M):
+    """test/multidimensional.jl:139-159 — 2-D 64x64, BKB, sigma = 1.25, block_size = 32 (several blocks),
+    threshold max(2 * 10^(-1.20 M), 4e-12) (:9-18); also blocking disabled (:160-163)."""
+    Ns, Np = (64, 64), 1000
+    rng = np.random.default_rng(4)
+    xs = [(rng.random(Np) * 2 * np.pi).astype(np.float64) for _ in Ns]
+    v = make_values(rng, Np, dtype)
+    thr = max(2 * 10.0 ** (-1.20 * M), 4e-12)
+    for block_size, blocked in ((32, True), (None, False)):
+        p = OraclePlan(dtype, Ns, m=M, sigma=1.25, block_size=block_size, use_blocked_spreading=blocked)
+        p.set_points(xs)
+        e1 = l2_error(p.exec_type1(v), nudft_type1(p.ks, xs, v))
+        assert e1 < thr
+        uk = make_values(rng, int(np.prod(p.size)), p.CT).reshape(p.size[::-1])
+        e2 = l2_error(p.exec_type2(uk), nudft_type2(p.ks, xs, uk, not p.is_complex))
+        assert e2 < thr
+
+
+def test_multidimensional_non_multiple_block():
+    """test/multidimensional.jl:171-180 — Ns = (37, 37), sigma = 2, block_size = 128 -> block (16, 8)."""
+    Ns, Np, M = (37, 37), 1000, 4
+    rng = np.random.default_rng(5)
+    xs = [(rng.random(Np) * 2 * np.pi) for _ in Ns]
+    v = make_values(rng, Np, np.float64)
+    p = OraclePlan(np.float64, Ns, m=M, sigma=2.0, block_size=128, use_blocked_spreading=True)
+    assert p.block_dims == (16, 8)
+    p.set_points(xs)
+    assert l2_error(p.exec_type1(v), nudft_type1(p.ks, xs, v)) < 6 * 10.0 ** (-1.9 * M)
+
+
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_near_2pi_cell_index(T):
+    """test/near_2pi.jl:19-46 — for x = prevfloat(2pi), trunc((x / L) * N) + 1 == N for N in 400:100:10000,
+    while other operation orders fail for some N."""
+    L = T(2) * T(np.pi)
+    x = np.nextafter(L, T(0))
+    suf = "_f32" if T == np.float32 else "_f64"
+    f = getattr(oracle.lib(), "orc_point_to_cell" + suf)
+    bad_dx = bad_inv = bad_nl = 0
+    for N in range(400, 10001, 100):
+        assert f(x, N, None) == N
+        dx = L / T(N)
+        bad_dx += int(T(x / dx)) + 1 != N
+        bad_inv += int(T(x * T(T(N) / L))) + 1 != N
+        bad_nl += int(T(T(x * T(N)) / L)) + 1 != N
+    assert bad_dx > 0 and bad_inv > 0 and bad_nl > 0     # the reference test asserts these orders DO fail
+
+
+def test_near_2pi_point_to_cell_thirds():
+    """test/near_2pi.jl:72-85."""
+    L = 2 * np.pi
+    f = oracle.lib().orc_point_to_cell_f64
+    assert f(np.nextafter(L / 3, 0.0), 3, None) == 1
+    assert f(np.nextafter(2 * L / 3, 0.0), 3, None) == 2
+    assert f(np.nextafter(L, 0.0), 3, None) == 3
+
+
+def test_near_2pi_nufft():
+    """test/near_2pi.jl:48-70 — x = prevfloat(2pi), v = 4.2 + 3im, N = 32, M = 8, sigma = 1.5, block_size = 16."""
+    x = np.array([np.nextafter(2 * np.pi, 0.0)])
+    v = np.array([4.2 + 3j])
+    for blocked in (True, False):
+        p = OraclePlan(np.complex128, 32, m=8, sigma=1.5, block_size=16, use_blocked_spreading=blocked)
+        p.set_points(x)
+        np.testing.assert_allclose(p.exec_type1(v), nudft_type1(p.ks, [x], v), rtol=1e-11)
+
+
+def test_near_pi():
+    """test/near_2pi.jl:89-114 — x = prevfloat(pi), v = 3.4, N = 16 real Float64, M = 4, sigma = 1.5: rtol 1e-5;
+    point_to_cell(x, 24) consistent with (i-1) dx <= x < i dx."""
+    x = np.nextafter(np.pi, 0.0)
+    i = oracle.lib().orc_point_to_cell_f64(x, 24, None)
+    dx = 2 * np.pi / 24
+    assert (i - 1) * dx <= x < i * dx
+    p = OraclePlan(np.float64, 16, m=4, sigma=1.5)
+    xs = np.array([x])
+    p.set_points(xs)
+    u = p.exec_type1(np.array([3.4]))
+    ue = nudft_type1(p.ks, [xs], np.array([3.4]))
+    assert np.linalg.norm(u - ue) <= 1e-5 * np.linalg.norm(ue)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_uniform_points(dtype):
+    """test/uniform_points.jl:17-52 — x_j = 2pi (j-1)/N, N = 256, M = 8, sigma = 1.25: type-1 == FFT (< 4e-10),
+    type-2 == unnormalised backward FFT (< 5e-10).  Pins sign and normalisation conventions (and pocketfft
+    standing in for FFTW)."""
+    N = 256
+    rng = np.random.default_rng(42)
+    x = (2 * np.pi * np.arange(N) / N)
+    v = make_values(rng, N, dtype)
+    if np.dtype(dtype).kind != "c":
+        u_fft = np.fft.rfft(v)
+        u_fft[-1] = 0
+        v = np.fft.irfft(u_fft, N)
+    else:
+        u_fft = np.fft.fft(v)
+    p = OraclePlan(dtype, N, m=8, sigma=1.25)
+    p.set_points(x)
+    assert l2_error(p.exec_type1(v), u_fft) < 4e-10
+    expected = v * N
+    assert l2_error(p.exec_type2(u_fft), expected) < 5e-10
+
+
+@pytest.mark.parametrize("kernel", ["bspline", "gaussian", "kaiser_bessel", "backwards_kaiser_bessel"])
+def test_approx_window_functions(kernel):
+    """test/approx_window_functions.jl:9-24 — sigma = 1.5, M = 4, N = 256, 1000 x in [0.8, 2.2] dx: fast and direct
+    evaluation give the same cell and values within rtol 1e-7."""
+    p = OraclePlan(np.float64, 170, m=4, sigma=1.5, kernel=kernel)     # N~ = nextprod(255) = 256
+    assert p.Nos[0] == 256
+    dx = 2 * np.pi / 256
+    for x in np.linspace(0.8, 2.2, 1000) * dx:
+        ia, a = p.evaluate_kernel(float(x), mode="fast")
+        ib, b = p.evaluate_kernel(float(x), mode="direct")
+        assert ia == ib
+        # `SVector(a) ≈ SVector(b) rtol=1e-7` is a NORM-wise comparison in Julia
+        assert np.linalg.norm(a - b) <= 1e-7 * max(np.linalg.norm(a), np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64])
+def test_callbacks(dtype):
+    """test/callbacks.jl:6-57 — 3-D (64, 32, 16), Np = prod/3, defaults; non-uniform callback v * weights[n],
+    uniform callback w / k^2 (0 at k = 0): fused == applied outside (isapprox, rtol sqrt(eps)); block_size in
+    (nothing, (8,8,8))."""
+    Ns = (64, 32, 16)
+    Np = int(np.prod(Ns)) // 3
+    rng = np.random.default_rng(42)
+    rt = np.float32
+    weights = rng.random(Np).astype(rt)
+    xs = [(rng.random(Np) * 2 * np.pi).astype(rt) for _ in Ns]
+    vp = make_values(rng, Np, dtype)
+    base = OraclePlan(dtype, Ns, block_size=None)
+    k2 = sum(np.asarray(k, dtype=np.float64).reshape([-1 if i == d else 1 for i in range(3)][::-1]) ** 2
+             for d, k in enumerate(base.ks))
+    factor = np.where(k2 == 0, 0.0, 1.0 / np.where(k2 == 0, 1.0, k2)).astype(rt)      # shape size[::-1]
+    base.set_points(xs)
+    t1 = base.exec_type1((vp * weights).astype(dtype)) * factor
+    t2 = base.exec_type2((t1 * factor).astype(base.CT)) * weights
+    rtol = np.sqrt(np.finfo(rt).eps)
+    for block_size, blocked in ((None, False), ((8, 8, 8), True)):
+        p = OraclePlan(dtype, Ns, block_size=block_size, use_blocked_spreading=blocked)
+        p.set_points(xs)
+        ws = p.exec_type1(vp, nu_weights=weights, u_factor=factor)
+        assert np.linalg.norm(ws - t1) <= rtol * np.linalg.norm(t1)
+        wp = p.exec_type2(ws, nu_weights=weights, u_factor=factor)
+        assert np.linalg.norm(wp - t2) <= rtol * np.linalg.norm(t2)
+
+
+def test_errors():
+    """test/errors.jl:4-11 — N = 12, sigma = 1.25, M = 8 -> ArgumentError (floor(sigma N) = 15 < 2M)."""
+    with pytest.raises(ValueError):
+        OraclePlan(np.complex128, 12, m=8, sigma=1.25)
+
+
+def test_oversampled_size_rule():
+    """src/plan.jl:485-498 worked examples: 256 -> 512 (sigma 2), 384 (1.5), 320 (1.25); real first dim even."""
+    assert oracle.oversampled_dims((256, 256, 256), 2.0, False, np.float32) == (512, 512, 512)
+    assert oracle.oversampled_dims((256,), 1.5, False, np.float64) == (384,)
+    assert oracle.oversampled_dims((256,), 1.25, True, np.float64) == (320,)
+    assert oracle.oversampled_dims((35, 64, 40), 1.5, False, np.float64) == (54, 96, 60)
+    assert oracle.oversampled_dims((37, 37), 2.0, True, np.float64) == (80, 75)    # 2*nextprod(floor(2*19)), nextprod(74)
+    assert oracle.nextprod235(74) == 75 and oracle.nextprod235(38) == 40 // 1
+
+
+def test_index_map_and_block_dims():
+    """src/NonuniformFFTs.jl:318-348 and src/plan.jl:437-451."""
+    assert list(oracle.non_oversampled_indices(4, 8, False, False)) == [0, 1, 6, 7]
+    assert list(oracle.non_oversampled_indices(4, 8, False, True)) == [6, 7, 0, 1]
+    assert list(oracle.non_oversampled_indices(5, 8, False, False)) == [0, 1, 2, 6, 7]
+    assert list(oracle.non_oversampled_indices(5, 8, False, True)) == [6, 7, 0, 1, 2]
+    assert list(oracle.non_oversampled_indices(3, 5, True, False)) == [0, 1, 2]
+    assert oracle.get_block_dims((512, 512, 512), 4096) == (16, 16, 16)
+    assert oracle.get_block_dims((74, 74), 128) == (16, 8)
+    assert oracle.get_block_dims((512,), 4096) == (4096,)
+
+
+def test_stable_sort_matches_definition():
+    """src/blocking/cpu.jl:73-111 in 1-thread order: perm sorted by (block id, original index)."""
+    rng = np.random.default_rng(0)
+    p = OraclePlan(np.float64, (20, 24, 18), sigma=1.5)
+    xs = [rng.standard_normal(5000) * 3 for _ in range(3)]
+    bid, cum, perm = p.sort_points(xs, (8, 4, 5))
+    order = np.lexsort((np.arange(5000), bid))
+    assert np.array_equal(perm, order)
+    assert np.array_equal(cum, np.concatenate([[0], np.cumsum(np.bincount(bid, minlength=len(cum) - 1))]))
