@@ -1,0 +1,56 @@
+"""CPU test: libnufft_b200.so loads and exports every symbol include/nufft_b200.h declares (no compute calls),
+and the ctypes structs mirror the C structs."""
+import ctypes as C
+import re
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def declared_functions():
+    text = (ROOT / "include" / "nufft_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nufft_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_boundary():
+    names = declared_functions()
+    for required in ("nufft_plan_create", "nufft_plan_destroy", "nufft_set_points", "nufft_exec_type1", "nufft_exec_type2",
+                     "nufft_plan_shape", "nufft_get_binning", "nufft_get_timings", "nufft_describe", "nufft_last_error"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    import nufft_b200  # noqa: F401
+    from nufft_b200 import _lib
+    lib = _lib.load()
+    names = declared_functions()
+    assert set(names) == set(_lib.SYMBOLS), "ctypes binding and header disagree"
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/nufft_b200.h but not exported"
+    assert lib.nufft_abi_version() == 1
+
+
+def test_opts_struct_layout_and_defaults():
+    import nufft_b200  # noqa: F401
+    from nufft_b200 import _lib
+    lib = _lib.load()
+    o = _lib.nufft_opts()
+    assert lib.nufft_opts_default(C.byref(o)) == 0
+    # the library writes sizeof(nufft_opts) as it sees it: must equal the ctypes mirror
+    assert o.struct_size == C.sizeof(_lib.nufft_opts)
+    assert (o.half_support, o.sigma, o.ntransforms) == (4, 2.0, 1)          # src/plan.jl:573,583
+    assert o.kernel == _lib.KERNEL_IDS["kaiser_bessel"] and o.eval_mode == _lib.EVAL_IDS["direct"]  # CUDA ext defaults
+    # a wrong struct_size is rejected without touching the GPU
+    o.struct_size = 8
+    h = C.c_void_p()
+    assert lib.nufft_plan_create(C.byref(h), C.byref(o)) == _lib.NUFFT_ERR_ARG
+    assert b"ABI mismatch" in lib.nufft_last_error()
+
+
+def test_no_cpu_fallback_in_product_package():
+    """The product package must not import the oracle (or any CPU compute path)."""
+    pkg = ROOT / "nonuniformffts.jl_b200"
+    for f in pkg.glob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f
