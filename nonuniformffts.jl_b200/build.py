@@ -23,7 +23,8 @@ LIB = HERE / "libnufft_b200.so"
 
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CFLAGS = ["-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-O2",
+DEV_M = os.environ.get("NUFFT_DEV_M")          # development only: instantiate a single half support
+CFLAGS = ([f"-DNUFFT_DEV_M={DEV_M}"] if DEV_M else []) + ["-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-O2",
           "-ccbin", shutil.which("g++") or "g++", "-Xptxas", "-v"]
 
 # (source, object suffix, extra defines)

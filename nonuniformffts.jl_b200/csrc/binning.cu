@@ -276,6 +276,15 @@ __global__ void work_items_kernel(const int32_t *__restrict__ bin_offsets, int64
     }
 }
 
+// item_table[item_start[b] + c] = (b, c) for every chunk c of bin b
+__global__ void item_table_kernel(const int32_t *__restrict__ item_start, int64_t nbins, int2 *__restrict__ table)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    const int s = item_start[b], e = item_start[b + 1];
+    for (int i = s; i < e; ++i) table[i] = make_int2((int)b, i - s);
+}
+
 // identity permutation when there is a single bin and nothing to sort
 __global__ void iota_kernel(int32_t *v, int64_t n)
 {
@@ -383,6 +392,14 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
     NUFFT_COUNT_LAUNCH();
     // inclusive scan of [0, n0, n1, ...]: item_start[b] = first item of bin b, item_start[nbins] = total
     NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_item_start, nb1, true));
+    const size_t max_items = (size_t)p.nbins + (size_t)cdiv(np, p.geom.chunk) + 1;
+    if (max_items > p.item_cap) {
+        if (p.d_item_table) cudaFree(p.d_item_table);
+        p.item_cap = max_items + max_items / 8;
+        CUDA_TRY(cudaMalloc(&p.d_item_table, p.item_cap * sizeof(int2)));
+    }
+    item_table_kernel<<<(unsigned)cdiv(p.nbins, 256), 256, 0, st>>>(p.d_item_start, p.nbins, p.d_item_table);
+    NUFFT_COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
     return NUFFT_SUCCESS;
 }

@@ -176,7 +176,9 @@ struct Plan {
     size_t hist_cap = 0;
     uint32_t *d_scan_tmp = nullptr;
     size_t scan_tmp_cap = 0;
-    int32_t *d_item_start = nullptr; // nbins + 1: exclusive scan of work items per bin
+    int32_t *d_item_start = nullptr; // nbins + 1: inclusive-scan form of work items per bin
+    int2 *d_item_table = nullptr;    // per work item: (bin, chunk index)
+    size_t item_cap = 0;
     int32_t *d_counters = nullptr;   // small block of device counters
 
     // timings
@@ -187,6 +189,14 @@ struct Plan {
 
     bool sticky_error = false;
 };
+
+// size (in T) of the per-point weight record of the shared-memory kernels (must match WRecord in tile_common.cuh)
+static inline int record_size(int D, int M)
+{
+    const int W = 2 * M, G = 32 / W, NI = (W + G - 1) / G;
+    const int wslot = (W + 3) / 4 * 4, yslot = (G * NI + 3) / 4 * 4;
+    return D == 1 ? wslot : (D == 2 ? 2 * wslot : 2 * wslot + yslot);
+}
 
 // kernel-launch helper: ceil-div
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -199,10 +199,10 @@ static std::vector<int32_t> build_index_map(int64_t Nk, int64_t Nos, bool r2c, b
 static constexpr int SMEM_PER_SM = 228 * 1024;
 static constexpr int SMEM_MAX_CTA = 227 * 1024;
 
+// per-CTA shared memory besides the tile: double-buffered batch (values, int4 starts, weight records) + tables
 size_t sm_batch_bytes(int D, int M, size_t real_bytes, size_t cell_bytes, int batch)
 {
-    // per point: D*2M weights (T) + 4 ints (starts + pad) + one value cell
-    return (size_t)batch * ((size_t)D * 2 * M * real_bytes + 16 + cell_bytes);
+    return (size_t)2 * batch * (cell_bytes + 16 + (size_t)record_size(D, M) * real_bytes);
 }
 
 // Shared-memory wavefronts needed by one warp-wide tile access of the spreading / interpolation kernels:
@@ -258,8 +258,11 @@ static bool choose_geometry(Plan &p)
         S[2] = S[0] * T[1];
         return (size_t)S[0] * T[1] * T[2] * cell_bytes;
     };
-    const size_t fixed = sm_batch_bytes(D, M, p.real_bytes, cell_bytes, g.batch) + (size_t)3 * p.cs_stride * p.real_bytes + 256;
+    const size_t fixed = sm_batch_bytes(D, M, p.real_bytes, cell_bytes, g.batch) + ((size_t)D * p.cs_stride + 4) * p.real_bytes + 128;
 
+    // bins never exceed N - (2M - 1) cells so that the padded tile fits in one period (T_d <= N_d): the kernels
+    // then wrap coordinates with a single conditional add/subtract (N >= 2M is guaranteed by check_nufft_size)
+    auto bcap = [&](int d) -> int64_t { return std::max<int64_t>(1, p.Nos[d] - (W - 1)); };
     bool user = false;
     for (int d = 0; d < D; ++d) if (p.opts.block_dims[d] > 0) user = true;
     int B[3] = {1, 1, 1}, T[3], S[3];
@@ -267,7 +270,7 @@ static bool choose_geometry(Plan &p)
     if (user) {
         for (int d = 0; d < D; ++d) {
             int64_t b = p.opts.block_dims[d] > 0 ? p.opts.block_dims[d] : 16;
-            B[d] = (int)std::min<int64_t>(b, p.Nos[d]);
+            B[d] = (int)std::min<int64_t>(b, bcap(d));
         }
         ok = tile_bytes(B, T, S) + fixed <= (size_t)SMEM_MAX_CTA;
     } else {
@@ -277,19 +280,19 @@ static bool choose_geometry(Plan &p)
         for (int pass = 0; pass < 2 && !ok; ++pass) {
             int best = 0;
             for (int b = 1; b <= bmax; ++b) {
-                for (int d = 0; d < D; ++d) B[d] = (int)std::min<int64_t>(b, p.Nos[d]);
+                for (int d = 0; d < D; ++d) B[d] = (int)std::min<int64_t>(b, bcap(d));
                 if (tile_bytes(B, T, S) + fixed <= budgets[pass]) best = b;
             }
             const int bmin = (D == 3) ? std::max(4, M) : 8;
             if (best >= bmin || (pass == 1 && best >= 2)) {
-                for (int d = 0; d < D; ++d) B[d] = (int)std::min<int64_t>(best, p.Nos[d]);
+                for (int d = 0; d < D; ++d) B[d] = (int)std::min<int64_t>(best, bcap(d));
                 ok = true;
             }
         }
     }
     if (!ok) {
         // shared-memory tiles unusable: bins only serve locality of the global-memory kernels
-        for (int d = 0; d < D; ++d) B[d] = (int)std::min<int64_t>(D == 1 ? 1024 : (D == 2 ? 32 : 8), p.Nos[d]);
+        for (int d = 0; d < D; ++d) B[d] = (int)std::min<int64_t>(D == 1 ? 1024 : (D == 2 ? 32 : 8), bcap(d));
     }
     tile_bytes(B, T, S);
     int64_t nbins = 1;
@@ -463,7 +466,7 @@ void host_plan_free(Plan &p)
     f(p.d_us); f(p.d_cs);
     for (int d = 0; d < 3; ++d) { f(p.d_phihat[d]); f(p.d_imap[d]); f(p.d_invmap[d]); f(p.d_xs[d]); }
     f(p.d_keys[0]); f(p.d_keys[1]); f(p.d_vals[0]); f(p.d_vals[1]);
-    f(p.d_bin_offsets); f(p.d_hist); f(p.d_scan_tmp); f(p.d_item_start); f(p.d_counters);
+    f(p.d_bin_offsets); f(p.d_hist); f(p.d_scan_tmp); f(p.d_item_start); f(p.d_item_table); f(p.d_counters);
     if (p.ev_ok) { for (int i = 0; i < 32; ++i) cudaEventDestroy(p.ev[i]); p.ev_ok = false; }
 }
 

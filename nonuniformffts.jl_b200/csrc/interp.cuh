@@ -3,23 +3,19 @@
 // Replaces src/interpolation/gpu.jl:4-38,124-193 (global-memory kernel) and :211-395 (shared-memory
 // kernel).  Values are scaled by prod_d dx_d (src/interpolation/gpu.jl:55-56).
 //
-// Shared-memory kernel: persistent CTAs pull (bin, chunk) work items; the bin's padded subgrid tile is
-// staged in dynamic shared memory (periodic wrap applied while loading); threads evaluate the kernel
-// values of a batch of points into shared memory; then one WARP per point computes the (2M)^D dot
-// product with lanes laid out as (2M consecutive x cells) x (32/2M rows) — conflict-free 64-byte row
-// segments — and reduces with warp shuffles; lane 0 scatters the result through the permutation.
+// Shared-memory kernel (sm_100a), v2: persistent CTAs pull (bin, chunk) work items; the bin's padded subgrid
+// tile is staged in dynamic shared memory (16-byte vector loads, periodic wrap applied per row/column);
+// producer warps evaluate the kernel values of batch b+1 while the consumer warps process batch b; one WARP per
+// point computes the (2M)^D dot product with lanes laid out as (2M consecutive x cells) x (32/2M rows) —
+// conflict-free row segments — and reduces with warp shuffles; lane 0 scatters the result through the
+// permutation (original point index carried in the per-point record).
 #pragma once
-#include "spread.cuh"
+#include "tile_common.cuh"
 
 namespace nufft {
 
 constexpr int INTERP_THREADS = 256;
-
-template <typename T, bool CPLX> __device__ __forceinline__ void store_value(void *vp, int64_t i, typename CellOf<T, CPLX>::type v)
-{
-    using Cell = typename CellOf<T, CPLX>::type;
-    ((Cell *)vp)[i] = v;
-}
+constexpr int INTERP_NPROD = 2;
 
 template <typename T, bool CPLX, int D, int M>
 __global__ void __launch_bounds__(128)
@@ -67,6 +63,29 @@ interp_gm_kernel(KernelParams<T> kp, int64_t np, const T *__restrict__ xs0, cons
     }
 }
 
+// 16-byte vector load of VEC consecutive cells (f32 types); scalar otherwise
+template <typename Cell> struct TileVec { static constexpr int VEC = 1; };
+template <> struct TileVec<float> { static constexpr int VEC = 4; };
+template <> struct TileVec<float2> { static constexpr int VEC = 2; };
+template <> struct TileVec<double> { static constexpr int VEC = 2; };
+
+__device__ __forceinline__ void ldg_vec(const float *p, float *v)
+{
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ldg_vec(const float2 *p, float2 *v)
+{
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = make_float2(t.x, t.y); v[1] = make_float2(t.z, t.w);
+}
+__device__ __forceinline__ void ldg_vec(const double *p, double *v)
+{
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+    v[0] = t.x; v[1] = t.y;
+}
+__device__ __forceinline__ void ldg_vec(const double2 *p, double2 *v) { v[0] = __ldg(p); }
+
 template <typename T, bool CPLX, int D, int M>
 __global__ void __launch_bounds__(INTERP_THREADS)
 interp_sm_kernel(KernelParams<T> kp, TileGeom g, SmArgs a, const T *__restrict__ xs0, const T *__restrict__ xs1,
@@ -74,117 +93,187 @@ interp_sm_kernel(KernelParams<T> kp, TileGeom g, SmArgs a, const T *__restrict__
                  int64_t ncells, T prefactor, const T *__restrict__ nu_weights)
 {
     using Cell = typename CellOf<T, CPLX>::type;
+    using LM = LaneMap<M>;
+    using REC = WRecord<D, M, false>;
     constexpr int W = 2 * M;
     constexpr int NT = INTERP_THREADS;
     constexpr int NWARP = NT / 32;
-    constexpr int WS = SmLayout<D, M>::WS;
-    constexpr int G = 32 / W;
-    constexpr int NI = (W + G - 1) / G;
+    constexpr int NCONS = NWARP - INTERP_NPROD;
+    constexpr int NPT = 32 * INTERP_NPROD;
+    constexpr int G = LM::G, NI = LM::NI;
+    constexpr int RS = REC::SIZE;
+    constexpr int VEC = TileVec<Cell>::VEC;
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tile_bytes = (g.tile_cells * (int)sizeof(Cell) + 15) & ~15;
     Cell *tile = (Cell *)smem_raw;
-    Cell *v_s = tile + g.tile_cells;          // unused here; keeps the layout of the spreading kernel
-    T *cs_s = (T *)(v_s + g.batch);
-    T *w_s = cs_s + D * kp.cs_stride;
-    int *st_s = (int *)(w_s + g.batch * WS);
-    __shared__ int s_item[4];
+    int4 *st_s = (int4 *)(smem_raw + tile_bytes);                     // [2][batch]: local starts + original index
+    Cell *v_s = (Cell *)(st_s + 2 * g.batch);                         // [2][batch]: .x = output scale of the point
+    T *rec_s = (T *)(v_s + 2 * g.batch);                              // [2][batch][RS]
+    T *cs_s = rec_s + 2 * g.batch * RS;
+    __shared__ int s_item[2][4];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool consumer = warp < NCONS;
+    const int ptid = tid - 32 * NCONS;
     const int lx = lane % W, lg = lane / W;
     const bool lane_on = lg < G;
-    const int Tx = g.T[0], Ty = g.T[1], Tz = g.T[2], Sx = g.S[0];
+    const int Tx = g.T[0], Ty = g.T[1], Tz = g.T[2], Sx = g.S[0], S2 = g.S[2];
     const int total_items = a.item_start[a.nbins];
 
     for (int i = tid; i < D * kp.cs_stride; i += NT) cs_s[i] = kp.cs[i];
+    if (tid == 0) {
+        const int item = atomicAdd(a.work_counter, 1);
+        s_item[0][0] = item;
+        if (item < total_items) decode_item(a, item, g.chunk, s_item[0][1], s_item[0][2], s_item[0][3]);
+    }
+    __syncthreads();
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
+    for (int it = 0;; ++it) {
+        const int *cur = s_item[it & 1];
+        if (cur[0] >= total_items) break;
+        const int bin = cur[1], k0 = cur[2], k1 = cur[3];
+        if (tid == NT - 1) {
+            int *nxt = s_item[(it + 1) & 1];
             const int item = atomicAdd(a.work_counter, 1);
-            s_item[0] = item;
-            if (item < total_items) decode_item(a, item, g.chunk, s_item[1], s_item[2], s_item[3]);
+            nxt[0] = item;
+            if (item < total_items) decode_item(a, item, g.chunk, nxt[1], nxt[2], nxt[3]);
         }
-        __syncthreads();
-        if (s_item[0] >= total_items) break;
-        const int bin = s_item[1], k0 = s_item[2], k1 = s_item[3];
         int b = bin;
         const int bx = b % g.nb[0]; b /= g.nb[0];
         const int by = b % g.nb[1]; b /= g.nb[1];
         const int bz = b;
-        const int org[3] = {bx * g.B[0], by * g.B[1], bz * g.B[2]};
+        const int org0 = bx * g.B[0], org1 = by * g.B[1], org2 = bz * g.B[2];
+        const int nbatches = (k1 - k0 + g.batch - 1) / g.batch;
 
         for (int c = 0; c < C; ++c) {
-            // ---- stage the padded tile (periodic wrap) ----------------------------------------
+            // ---- producer: one thread per point ---------------------------------------------------------
+            auto produce = [&](int bi) {
+                const int kb = k0 + bi * g.batch;
+                const int nb = min(g.batch, k1 - kb);
+                int4 *st_b = st_s + (bi & 1) * g.batch;
+                Cell *v_b = v_s + (bi & 1) * g.batch;
+                T *rec_b = rec_s + (bi & 1) * g.batch * RS;
+                for (int p = ptid; p < nb; p += NPT) {
+                    const int32_t n = a.perm[kb + p];
+                    const T x0 = xs0[kb + p];
+                    const T x1 = D > 1 ? xs1[kb + p] : (T)0;
+                    const T x2 = D > 2 ? xs2[kb + p] : (T)0;
+                    const T scale = prefactor * (nu_weights ? nu_weights[n] : (T)1);
+                    int4 st = make_int4(0, 0, 0, n);
+                    T w[W];
+                    st.x = eval_kernel_values<T, M>(kp, cs_s, 0, x0, w) - org0;
+                    REC::store(rec_b + p * RS, 0, w, st.x);
+                    if (D > 1) {
+                        st.y = eval_kernel_values<T, M>(kp, cs_s + kp.cs_stride, 1, x1, w) - org1;
+                        REC::store(rec_b + p * RS, 1, w, st.y);
+                    }
+                    if (D > 2) {
+                        st.z = eval_kernel_values<T, M>(kp, cs_s + 2 * kp.cs_stride, 2, x2, w) - org2;
+                        REC::store(rec_b + p * RS, 2, w, st.z);
+                    }
+                    st_b[p] = st;
+                    reinterpret_cast<T *>(v_b + p)[0] = scale;
+                }
+            };
+            if (!consumer) produce(0);
+            // ---- stage the padded tile (periodic wrap; host guarantees T_d <= N_d), all warps --------------
             {
                 const Cell *u = us + (int64_t)c * ncells;
-                const int x0 = org[0] - (M - 1), y0 = org[1] - (M - 1), z0 = org[2] - (M - 1);
-                const int rows = Ty * Tz;
-                for (int row = warp; row < rows; row += NWARP) {
-                    const int z = row / Ty, y = row - z * Ty;
-                    const int gy = D > 1 ? wrap_index(y0 + y, g.N[1]) : 0;
-                    const int gz = D > 2 ? wrap_index(z0 + z, g.N[2]) : 0;
-                    const Cell *grow = u + ((int64_t)gz * g.N[1] + gy) * g.N[0];
-                    Cell *trow = tile + (size_t)z * g.S[2] + (size_t)y * Sx;
-                    for (int x = lane; x < Tx; x += 32) trow[x] = grow[wrap_index(x0 + x, g.N[0])];
-                }
-            }
-            for (int kb = k0; kb < k1; kb += g.batch) {
-                const int nb = min(g.batch, k1 - kb);
-                __syncthreads();
-                for (int t = tid; t < g.batch * D; t += NT) {
-                    const int d = t / g.batch, p = t - d * g.batch;
-                    if (p >= nb) continue;
-                    const T *xs = d == 0 ? xs0 : (d == 1 ? xs1 : xs2);
-                    T w[W];
-                    const int i0 = eval_kernel_values<T, M>(kp, cs_s + d * kp.cs_stride, d, xs[kb + p], w);
-                    st_s[p * 4 + d] = i0 - org[d];
-                    T *dst = w_s + p * WS + d * W;
+                const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
+                const int x0 = org0 - (M - 1), y0 = D > 1 ? org1 - (M - 1) : 0, z0 = D > 2 ? org2 - (M - 1) : 0;
+                const bool vec_ok = VEC > 1 && (Nx % VEC) == 0;
+                const int a0 = vec_ok ? pmod(x0, VEC) : 0;
+                const int nvec = vec_ok ? (Tx + a0 + VEC - 1) / VEC : Tx;
+                for (int z = 0; z < Tz; ++z) {
+                    const int gz = D > 2 ? wrap1(z0 + z, Nz) : 0;
+                    for (int y = warp; y < Ty; y += NWARP) {
+                        const int gy = D > 1 ? wrap1(y0 + y, Ny) : 0;
+                        const Cell *grow = u + ((int64_t)gz * Ny + gy) * Nx;
+                        Cell *trow = tile + z * S2 + y * Sx;
+                        if (vec_ok) {
+                            for (int q = lane; q < nvec; q += 32) {
+                                const int xt = VEC * q - a0;
+                                Cell val[VEC];
+                                ldg_vec(grow + wrap1(x0 + xt, Nx), val);
 #pragma unroll
-                    for (int j = 0; j < W; ++j) dst[j] = w[j];
-                }
-                __syncthreads();
-                for (int p = warp; p < nb; p += NWARP) {
-                    const int *st = st_s + p * 4;
-                    const T *wp = w_s + p * WS;
-                    Cell acc = cell_zero((Cell *)nullptr);
-                    if constexpr (D == 3) {
-                        const int sx = st[0], sy = st[1], sz = st[2];
-                        const Cell *base = tile + (size_t)sz * g.S[2] + (size_t)sy * Sx + sx + lx;
-                        T wyr[NI];
-#pragma unroll
-                        for (int i = 0; i < NI; ++i) wyr[i] = (lane_on && lg + i * G < W) ? wp[W + lg + i * G] : (T)0;
-#pragma unroll
-                        for (int jz = 0; jz < W; ++jz) {
-                            const T wz = wp[2 * W + jz];
-#pragma unroll
-                            for (int i = 0; i < NI; ++i) {
-                                const int jy = lg + i * G;
-                                if (lane_on && jy < W) cfma(acc, base[(size_t)jz * g.S[2] + jy * Sx], wyr[i] * wz);
+                                for (int e = 0; e < VEC; ++e) {
+                                    const int x = xt + e;
+                                    if (x >= 0 && x < Tx) trow[x] = val[e];
+                                }
                             }
+                        } else {
+                            for (int x = lane; x < Tx; x += 32) trow[x] = grow[wrap1(x0 + x, Nx)];
                         }
-                        acc = cmul(acc, lane_on ? wp[lx] : (T)0);
-                    } else if constexpr (D == 2) {
-                        const int sx = st[0], sy = st[1];
-                        const Cell *base = tile + (size_t)sy * Sx + sx + lx;
-#pragma unroll
-                        for (int i = 0; i < NI; ++i) {
-                            const int jy = lg + i * G;
-                            if (lane_on && jy < W) cfma(acc, base[jy * Sx], wp[W + jy]);
-                        }
-                        acc = cmul(acc, lane_on ? wp[lx] : (T)0);
-                    } else {
-                        const int sx = st[0];
-                        if (lane < W) acc = cmul(tile[sx + lane], wp[lane]);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc = cadd(acc, shfl_xor(acc, o));
-                    if (lane == 0) {
-                        const int32_t n = a.perm[kb + p];
-                        const T scale = prefactor * (nu_weights ? nu_weights[n] : (T)1);
-                        store_value<T, CPLX>(vp.p[c], n, cmul(acc, scale));
                     }
                 }
             }
             __syncthreads();
+            for (int bi = 0; bi < nbatches; ++bi) {
+                if (!consumer) {
+                    if (bi + 1 < nbatches) produce(bi + 1);
+                } else {
+                    const int nb = min(g.batch, k1 - (k0 + bi * g.batch));
+                    const int4 *st_b = st_s + (bi & 1) * g.batch;
+                    const Cell *v_b = v_s + (bi & 1) * g.batch;
+                    const T *rec_b = rec_s + (bi & 1) * g.batch * RS;
+                    for (int p = warp; p < nb; p += NCONS) {
+                        const int4 st = st_b[p];
+                        const T *wp = rec_b + p * RS;
+                        Cell acc = cell_zero((Cell *)nullptr);
+                        if constexpr (D == 3) {
+                            constexpr int ZV = (W % 4 == 0) ? 4 : 2;
+                            T wy[NI], wz[W];
+                            VecLoad<T, NI>::load(wp + REC::OFF_Y + lg * NI, wy);
+#pragma unroll
+                            for (int j = 0; j < W; j += ZV) VecLoad<T, ZV>::load(wp + REC::OFF_Z + j, wz + j);
+                            const T wx = wp[lx];
+                            const Cell *c0 = tile + st.z * S2 + (st.y + lg) * Sx + st.x + lx;
+                            const int dSx = G * Sx;
+                            if (lane_on) {
+                                constexpr int ZC = (NI * W <= 16) ? W : ((NI * 4 <= 16) ? 4 : (NI <= 8 ? 2 : 1));  // planes per chunk
+#pragma unroll
+                                for (int zb = 0; zb < W; zb += ZC) {
+                                    Cell cell[ZC][NI];
+#pragma unroll
+                                    for (int jz = 0; jz < ZC; ++jz)
+#pragma unroll
+                                        for (int i = 0; i < NI; ++i)
+                                            if (lg + i * G < W) cell[jz][i] = c0[(zb + jz) * S2 + i * dSx];
+#pragma unroll
+                                    for (int jz = 0; jz < ZC; ++jz) {
+                                        Cell pl = cell_zero((Cell *)nullptr);
+#pragma unroll
+                                        for (int i = 0; i < NI; ++i)
+                                            if (lg + i * G < W) cfma(pl, cell[jz][i], wy[i]);
+                                        cfma(acc, pl, wz[zb + jz]);
+                                    }
+                                }
+                                acc = cmul(acc, wx);
+                            }
+                        } else if constexpr (D == 2) {
+                            const Cell *c0 = tile + (st.y + lg) * Sx + st.x + lx;
+                            if (lane_on) {
+#pragma unroll
+                                for (int i = 0; i < NI; ++i) {
+                                    const int jy = lg + i * G;
+                                    if (jy < W) cfma(acc, c0[i * G * Sx], wp[REC::OFF_Y + jy]);
+                                }
+                                acc = cmul(acc, wp[lx]);
+                            }
+                        } else {
+                            if (lane < W) acc = cmul(tile[st.x + lane], wp[lane]);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc = cadd(acc, shfl_xor(acc, o));
+                        if (lane == 0) {
+                            const T scale = reinterpret_cast<const T *>(v_b + p)[0];
+                            store_value<T, CPLX>(vp.p[c], st.w, cmul(acc, scale));
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
 }

@@ -35,13 +35,13 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
             NUFFT_COUNT_LAUNCH();
         } else {
             auto kern = interp_sm_kernel<T, CPLX, D, M>;
-            const size_t smem = sm_dynamic_bytes<T, CPLX, D, M>(p.geom, p.cs_stride);
+            const size_t smem = sm_dynamic_bytes<T, CPLX, D, M, false>(p.geom, p.cs_stride);
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 0, nsm = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, INTERP_THREADS, smem));
             CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
             if (occ < 1) { set_error("interp_sm_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
-            SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_counters, (int)p.nbins};
+            SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
             CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
             kern<<<nsm * occ, INTERP_THREADS, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, prefactor, nuw);
             NUFFT_COUNT_LAUNCH();
@@ -51,6 +51,10 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
     return NUFFT_SUCCESS;
 }
 
+// NUFFT_DEV_M=<M> (development builds only) restricts the instantiated half supports to one value
+#ifdef NUFFT_DEV_M
+#define NUFFT_M_CASES(D_) case NUFFT_DEV_M: return interp_launch<T, CPLX, D_, NUFFT_DEV_M>(p, vp, cb);
+#else
 #define NUFFT_M_CASES(D_) \
     case 2: return interp_launch<T, CPLX, D_, 2>(p, vp, cb);   \
     case 3: return interp_launch<T, CPLX, D_, 3>(p, vp, cb);   \
@@ -60,9 +64,10 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
     case 7: return interp_launch<T, CPLX, D_, 7>(p, vp, cb);   \
     case 8: return interp_launch<T, CPLX, D_, 8>(p, vp, cb);   \
     case 9: return interp_launch<T, CPLX, D_, 9>(p, vp, cb);   \
-    case 10: return interp_launch<T, CPLX, D_, 10>(p, vp, cb); \
-    case 11: return interp_launch<T, CPLX, D_, 11>(p, vp, cb); \
+    case 10: return interp_launch<T, CPLX, D_, 10>(p, vp, cb);   \
+    case 11: return interp_launch<T, CPLX, D_, 11>(p, vp, cb);   \
     case 12: return interp_launch<T, CPLX, D_, 12>(p, vp, cb);
+#endif
 
 template <typename T, bool CPLX> int interp_dispatch(Plan &p, void *const vp[], const nufft_callbacks *cb)
 {

@@ -33,15 +33,15 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
             NUFFT_COUNT_LAUNCH();
         } else {
             auto kern = spread_sm_kernel<T, CPLX, D, M>;
-            const size_t smem = sm_dynamic_bytes<T, CPLX, D, M>(p.geom, p.cs_stride);
+            const size_t smem = sm_dynamic_bytes<T, CPLX, D, M, true>(p.geom, p.cs_stride);
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int occ = 0, nsm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * M, smem));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (M + SPREAD_NPROD), smem));
             CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
             if (occ < 1) { set_error("spread_sm_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
-            SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_counters, (int)p.nbins};
+            SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
             CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
-            kern<<<nsm * occ, 32 * M, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, nuw);
+            kern<<<nsm * occ, 32 * (M + SPREAD_NPROD), smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, nuw);
             NUFFT_COUNT_LAUNCH();
         }
     }
@@ -49,6 +49,10 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
     return NUFFT_SUCCESS;
 }
 
+// NUFFT_DEV_M=<M> (development builds only) restricts the instantiated half supports to one value
+#ifdef NUFFT_DEV_M
+#define NUFFT_M_CASES(D_) case NUFFT_DEV_M: return spread_launch<T, CPLX, D_, NUFFT_DEV_M>(p, vp, cb);
+#else
 #define NUFFT_M_CASES(D_) \
     case 2: return spread_launch<T, CPLX, D_, 2>(p, vp, cb);   \
     case 3: return spread_launch<T, CPLX, D_, 3>(p, vp, cb);   \
@@ -58,9 +62,10 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
     case 7: return spread_launch<T, CPLX, D_, 7>(p, vp, cb);   \
     case 8: return spread_launch<T, CPLX, D_, 8>(p, vp, cb);   \
     case 9: return spread_launch<T, CPLX, D_, 9>(p, vp, cb);   \
-    case 10: return spread_launch<T, CPLX, D_, 10>(p, vp, cb); \
-    case 11: return spread_launch<T, CPLX, D_, 11>(p, vp, cb); \
+    case 10: return spread_launch<T, CPLX, D_, 10>(p, vp, cb);   \
+    case 11: return spread_launch<T, CPLX, D_, 11>(p, vp, cb);   \
     case 12: return spread_launch<T, CPLX, D_, 12>(p, vp, cb);
+#endif
 
 template <typename T, bool CPLX> int spread_dispatch(Plan &p, const void *const vp[], const nufft_callbacks *cb)
 {
