@@ -13,6 +13,7 @@
 //   tile geometry                replaces src/gpu_common.jl:19-92 (48 KiB static smem) with a
 //                                227 KiB dynamic shared-memory budget on sm_100a
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include "common.cuh"
@@ -248,6 +249,10 @@ static bool choose_geometry(Plan &p)
     const size_t cell_bytes = p.real_bytes * (p.cplx ? 2 : 1);
     g.D = D;
     g.batch = 64;
+    if (const char *e = getenv("NUFFT_B200_BATCH")) {          // tuning knob (multiple of 32, >= 32)
+        const int v = atoi(e);
+        if (v >= 32 && v <= 1024) g.batch = v / 32 * 32;
+    }
     g.chunk = p.opts.spread_chunk > 0 ? p.opts.spread_chunk : 4096;
     for (int d = 0; d < 3; ++d) { g.N[d] = (int)p.Nos[d]; g.B[d] = 1; g.nb[d] = 1; g.T[d] = 1; g.S[d] = 1; }
 

@@ -177,36 +177,28 @@ interp_sm_kernel(KernelParams<T> kp, TileGeom g, SmArgs a, const T *__restrict__
                 }
             };
             if (!consumer) produce(0);
-            // ---- stage the padded tile (periodic wrap; host guarantees T_d <= N_d), all warps --------------
+            // ---- stage the padded tile with asynchronous copies (cp.async / LDGSTS, one cell per lane; periodic
+            //      wrap per row/column; host guarantees T_d <= N_d).  All copies of a thread are in flight at once;
+            //      the producers' kernel evaluation above overlaps with them. -------------------------------------
             {
                 const Cell *u = us + (int64_t)c * ncells;
                 const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
                 const int x0 = org0 - (M - 1), y0 = D > 1 ? org1 - (M - 1) : 0, z0 = D > 2 ? org2 - (M - 1) : 0;
-                const bool vec_ok = VEC > 1 && (Nx % VEC) == 0;
-                const int a0 = vec_ok ? pmod(x0, VEC) : 0;
-                const int nvec = vec_ok ? (Tx + a0 + VEC - 1) / VEC : Tx;
-                for (int z = 0; z < Tz; ++z) {
-                    const int gz = D > 2 ? wrap1(z0 + z, Nz) : 0;
-                    for (int y = warp; y < Ty; y += NWARP) {
-                        const int gy = D > 1 ? wrap1(y0 + y, Ny) : 0;
-                        const Cell *grow = u + ((int64_t)gz * Ny + gy) * Nx;
-                        Cell *trow = tile + z * S2 + y * Sx;
-                        if (vec_ok) {
-                            for (int q = lane; q < nvec; q += 32) {
-                                const int xt = VEC * q - a0;
-                                Cell val[VEC];
-                                ldg_vec(grow + wrap1(x0 + xt, Nx), val);
-#pragma unroll
-                                for (int e = 0; e < VEC; ++e) {
-                                    const int x = xt + e;
-                                    if (x >= 0 && x < Tx) trow[x] = val[e];
-                                }
-                            }
-                        } else {
-                            for (int x = lane; x < Tx; x += 32) trow[x] = grow[wrap1(x0 + x, Nx)];
+                for (int xb = 0; xb < Tx; xb += 32) {
+                    const int x = xb + lane;
+                    const bool in = x < Tx;
+                    const int gx = wrap1(x0 + (in ? x : 0), Nx);
+                    for (int z = 0; z < Tz; ++z) {
+                        const int gz = D > 2 ? wrap1(z0 + z, Nz) : 0;
+                        const Cell *gplane = u + (int64_t)gz * Ny * Nx + gx;
+                        Cell *tplane = tile + z * S2 + x;
+                        for (int y = warp; y < Ty; y += NWARP) {
+                            const int gy = D > 1 ? wrap1(y0 + y, Ny) : 0;
+                            if (in) cp_async_cell<(int)sizeof(Cell)>(tplane + y * Sx, gplane + (int64_t)gy * Nx);
                         }
                     }
                 }
+                cp_async_wait_all();
             }
             __syncthreads();
             for (int bi = 0; bi < nbatches; ++bi) {

@@ -292,37 +292,52 @@ spread_sm_kernel(KernelParams<T> kp, TileGeom g, SmArgs a, const T *__restrict__
                 __syncthreads();
             }
             // ---- flush: tile -> global grid (periodic), vector reductions; re-zero the tile ------------
-            // (host guarantees T_d <= N_d, so a single conditional wrap per coordinate suffices)
+            // (host guarantees T_d <= N_d, so a single conditional wrap per coordinate suffices).
+            // Half-warps take one tile row each; a lane owns one 16-byte vector slot of the row, so everything
+            // that depends on x is computed once per work item.
             {
                 Cell *u = us + (int64_t)c * ncells;
                 const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
                 const int x0 = org0 - (M - 1), y0 = D > 1 ? org1 - (M - 1) : 0, z0 = D > 2 ? org2 - (M - 1) : 0;
                 const Cell zero = cell_zero((Cell *)nullptr);
                 const bool vec_ok = VEC > 1 && (Nx % VEC) == 0;
-                const int a0 = vec_ok ? pmod(x0, VEC) : 0;        // tile x of vector q starts at VEC * q - a0
-                const int nvec = vec_ok ? (Tx + a0 + VEC - 1) / VEC : Tx;
-                for (int z = 0; z < Tz; ++z) {
-                    const int gz = D > 2 ? wrap1(z0 + z, Nz) : 0;
-                    for (int y = warp; y < Ty; y += NWARP) {
-                        const int gy = D > 1 ? wrap1(y0 + y, Ny) : 0;
-                        Cell *grow = u + ((int64_t)gz * Ny + gy) * Nx;
-                        Cell *trow = tile + z * S2 + y * Sx;
-                        if (vec_ok) {
-                            for (int q = lane; q < nvec; q += 32) {
-                                const int xt = VEC * q - a0;
+                const int hl = lane & 15, hrow = lane >> 4;
+                if (vec_ok) {
+                    const int a0 = pmod(x0, VEC);                  // tile x of vector q starts at VEC * q - a0
+                    const int nvec = (Tx + a0 + VEC - 1) / VEC;
+                    for (int qb = 0; qb < nvec; qb += 16) {
+                        const int q = qb + hl;
+                        const int xt = VEC * q - a0;
+                        const int gx = wrap1(x0 + xt, Nx);
+                        bool in[VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) in[e] = q < nvec && xt + e >= 0 && xt + e < Tx;
+                        for (int z = 0; z < Tz; ++z) {
+                            const int gz = D > 2 ? wrap1(z0 + z, Nz) : 0;
+                            Cell *gplane = u + (int64_t)gz * Ny * Nx + gx;
+                            Cell *tplane = tile + z * S2 + xt;
+                            for (int y = 2 * warp + hrow; y < Ty; y += 2 * NWARP) {
+                                const int gy = D > 1 ? wrap1(y0 + y, Ny) : 0;
+                                Cell *trow = tplane + y * Sx;
                                 Cell val[VEC];
                                 bool nz = false;
 #pragma unroll
                                 for (int e = 0; e < VEC; ++e) {
-                                    const int x = xt + e;
-                                    const bool in = x >= 0 && x < Tx;
-                                    val[e] = in ? trow[x] : zero;
-                                    if (in) trow[x] = zero;
+                                    val[e] = zero;
+                                    if (in[e]) { val[e] = trow[e]; trow[e] = zero; }
                                     nz = nz || cnonzero(val[e]);
                                 }
-                                if (nz) red_vec(grow + wrap1(x0 + xt, Nx), val);
+                                if (nz) red_vec(gplane + (int64_t)gy * Nx, val);
                             }
-                        } else {
+                        }
+                    }
+                } else {
+                    for (int z = 0; z < Tz; ++z) {
+                        const int gz = D > 2 ? wrap1(z0 + z, Nz) : 0;
+                        for (int y = warp; y < Ty; y += NWARP) {
+                            const int gy = D > 1 ? wrap1(y0 + y, Ny) : 0;
+                            Cell *grow = u + ((int64_t)gz * Ny + gy) * Nx;
+                            Cell *trow = tile + z * S2 + y * Sx;
                             for (int x = lane; x < Tx; x += 32) {
                                 const Cell val = trow[x];
                                 trow[x] = zero;

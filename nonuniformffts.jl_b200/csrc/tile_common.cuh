@@ -140,6 +140,22 @@ template <> struct VecLoad<double, 8> {
     }
 };
 
+// asynchronous global -> shared copy of one cell (LDGSTS; completion via cp_async_wait_all)
+template <int BYTES> __device__ __forceinline__ void cp_async_cell(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 template <typename T, bool CPLX> __device__ __forceinline__ typename CellOf<T, CPLX>::type load_value(const void *vp, int64_t i)
 {
     using Cell = typename CellOf<T, CPLX>::type;

@@ -18,6 +18,7 @@ ap.add_argument("--m", type=int, default=4)
 ap.add_argument("--sigma", type=float, default=2.0)
 ap.add_argument("--method", default="auto")
 ap.add_argument("--dist", default="uniform")
+ap.add_argument("--block", default="")
 a = ap.parse_args()
 bench.N_MODES = a.modes
 xs, vp, uk = bench.make_inputs(3, a.np)
@@ -28,8 +29,9 @@ dev = torch.device("cuda", 0)
 xs_d = [torch.from_numpy(x).to(dev) for x in xs]
 vp_d, uk_d = torch.from_numpy(vp).to(dev), torch.from_numpy(uk).to(dev)
 plan = nb.PlanNUFFT(torch.complex64, (a.modes,) * 3, m=a.m, sigma=a.sigma, kernel=nb.BackwardsKaiserBesselKernel(),
-                    kernel_evalmode=nb.FastApproximation(), timer=True, gpu_method=a.method)
-print(plan)
+                    kernel_evalmode=nb.FastApproximation(), timer=True, gpu_method=a.method,
+                    block_size=tuple(int(b) for b in a.block.split(',')) if a.block else None)
+print(repr(plan).splitlines()[-3:])
 out1 = torch.empty((a.modes,) * 3, dtype=torch.complex64, device=dev)
 out2 = torch.empty(a.np, dtype=torch.complex64, device=dev)
 for it in range(a.iters):
