@@ -199,29 +199,23 @@ def run_ours(args):
                         kernel=nb.BackwardsKaiserBesselKernel(), kernel_evalmode=nb.FastApproximation(),
                         timer=True, device=dev)
 
+    pp = nb.PointPartitionedNUFFT(plan)     # N > 1: type-1 partial outputs all-reduced, type-2 spectrum broadcast
+
     def step_device():
-        plan.set_points(tuple(xs_d))
-        plan.exec_type1(out1_d, vp_d)
-        if world > 1:
-            dist.all_reduce(out1_d)                      # sum of the per-rank partial type-1 results (NVLink)
-        plan.set_points(tuple(xs_d))
-        if world > 1:
-            dist.broadcast(uk_d, src=0)                  # type-2: spectrum broadcast, points split
-        plan.exec_type2(out2_d, uk_d)
+        pp.set_points(tuple(xs_d))
+        pp.exec_type1(out1_d, vp_d)
+        pp.set_points(tuple(xs_d))
+        pp.exec_type2(out2_d, uk_d, src=0)
 
     def step_e2e():
         xd = [x.to(dev, non_blocking=True) for x in xs_pin]
         vd = vp_pin.to(dev, non_blocking=True)
-        plan.set_points(tuple(xd))
-        plan.exec_type1(out1_d, vd)
-        if world > 1:
-            dist.all_reduce(out1_d)
+        pp.set_points(tuple(xd))
+        pp.exec_type1(out1_d, vd)
         out1_pin.copy_(out1_d, non_blocking=True)
         ud = uk_pin.to(dev, non_blocking=True)
-        plan.set_points(tuple(xd))
-        if world > 1:
-            dist.broadcast(ud, src=0)
-        plan.exec_type2(out2_d, ud)
+        pp.set_points(tuple(xd))
+        pp.exec_type2(out2_d, ud, src=0)
         out2_pin.copy_(out2_d, non_blocking=True)
         torch.cuda.current_stream().synchronize()        # the caller reads the host results
 

@@ -231,14 +231,16 @@ interp_sm_kernel(KernelParams<T> kp, TileGeom g, SmArgs a, const T *__restrict__
                                     for (int jz = 0; jz < ZC; ++jz)
 #pragma unroll
                                         for (int i = 0; i < NI; ++i)
-                                            if (lg + i * G < W) cell[jz][i] = c0[(zb + jz) * S2 + i * dSx];
+                                            if (zb + jz < W && lg + i * G < W) cell[jz][i] = c0[(zb + jz) * S2 + i * dSx];
 #pragma unroll
                                     for (int jz = 0; jz < ZC; ++jz) {
-                                        Cell pl = cell_zero((Cell *)nullptr);
+                                        if (zb + jz < W) {
+                                            Cell pl = cell_zero((Cell *)nullptr);
 #pragma unroll
-                                        for (int i = 0; i < NI; ++i)
-                                            if (lg + i * G < W) cfma(pl, cell[jz][i], wy[i]);
-                                        cfma(acc, pl, wz[zb + jz]);
+                                            for (int i = 0; i < NI; ++i)
+                                                if (lg + i * G < W) cfma(pl, cell[jz][i], wy[i]);
+                                            cfma(acc, pl, wz[zb + jz]);
+                                        }
                                     }
                                 }
                                 acc = cmul(acc, wx);
