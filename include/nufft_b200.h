@@ -122,6 +122,13 @@ int  nufft_set_points(nufft_plan plan, int64_t np, const void *const x[/*dim*/])
 int  nufft_get_binning(nufft_plan plan, const int32_t **perm, const int32_t **bin_offsets,
                        int64_t *nbins, int64_t bin_dims[3]);
 
+/* The order the kernels actually use.  Plans on the register-tile fast path (3-D, Float32, HalfSupport(4)) refine every
+ * bin into sub-bins of 4x4x4 cells and sort by key = bin * nsub + ((sy * sub_dims[0] + sx) * sub_dims[2] + sz) (stable),
+ * a refinement of the reference order; nufft_get_binning then rebuilds the bin-stable permutation on demand.
+ * Other plans: nsub = 1 and both getters agree.  fine_offsets has nfine + 1 entries. */
+int  nufft_get_binning_fine(nufft_plan plan, const int32_t **perm, const int32_t **fine_offsets,
+                            int64_t *nfine, int64_t sub_dims[3]);
+
 /* ---- exec_type1!(us_k, p, vp; callbacks): src/NonuniformFFTs.jl:148-195 ---- */
 int  nufft_exec_type1(nufft_plan plan, void *const uhat[/*C*/], const void *const vp[/*C*/],
                       const nufft_callbacks *cb);

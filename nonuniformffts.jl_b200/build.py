@@ -25,7 +25,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 DEV_M = os.environ.get("NUFFT_DEV_M")          # development only: instantiate a single half support
 CFLAGS = ([f"-DNUFFT_DEV_M={DEV_M}"] if DEV_M else []) + ["-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-O2",
-          "-ccbin", shutil.which("g++") or "g++", "-Xptxas", "-v"]
+          "-ccbin", shutil.which("g++") or "g++", "-Xptxas", "-v", "-Xfatbin", "-compress-all"]
 
 # (source, object suffix, extra defines)
 UNITS = [("api.cu", "", []), ("host_plan.cu", "", []), ("binning.cu", "", []), ("deconv.cu", "", [])]

@@ -170,10 +170,22 @@ int nufft_get_binning(nufft_plan h, const int32_t **perm, const int32_t **bin_of
     NUFFT_TRY(check_plan(h));
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (p.Np < 0) { set_error("set_points has not been called"); return NUFFT_ERR_STATE; }
-    if (perm) *perm = p.d_perm;
+    if (perm) NUFFT_TRY(binning_coarse_perm(p, perm));     // rt plans: reference-order permutation rebuilt on demand
     if (bin_offsets) *bin_offsets = p.d_bin_offsets;
     if (nbins) *nbins = p.nbins;
     if (bin_dims) for (int d = 0; d < 3; ++d) bin_dims[d] = p.geom.B[d];
+    return NUFFT_SUCCESS;
+}
+
+int nufft_get_binning_fine(nufft_plan h, const int32_t **perm, const int32_t **fine_offsets, int64_t *nfine, int64_t sub_dims[3])
+{
+    NUFFT_TRY(check_plan(h));
+    Plan &p = *reinterpret_cast<Plan *>(h);
+    if (p.Np < 0) { set_error("set_points has not been called"); return NUFFT_ERR_STATE; }
+    if (perm) *perm = p.d_perm;
+    if (fine_offsets) *fine_offsets = p.d_fine_offsets;
+    if (nfine) *nfine = p.nbins * p.geom.nsub;
+    if (sub_dims) for (int d = 0; d < 3; ++d) sub_dims[d] = p.geom.sub[d];
     return NUFFT_SUCCESS;
 }
 

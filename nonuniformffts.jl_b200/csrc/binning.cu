@@ -15,6 +15,8 @@
 //   radix_scatter_kernel stable scatter (warp match_any ranks + per-warp digit counters)
 //   gather_points_kernel sorted, folded copy of the coordinates (coalesced reads in spread/interp)
 //   work_items_kernel    items per bin = ceil(count / chunk) (bins over `chunk` points are split)
+#include <algorithm>
+#include <utility>
 #include "common.cuh"
 #include "kernel_eval.cuh"
 
@@ -33,6 +35,9 @@ struct BinGeom {
     int B[3];
     int nb[3];
     int convention;
+    int rt;          // sub-bin refinement active (TileGeom::rt)
+    int sub[3];
+    int nsub;
 };
 
 // ---- keys --------------------------------------------------------------------------------------
@@ -50,15 +55,23 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
         if (valid) {
             T r;
             int c = point_to_cell0<T>(fold_point<T>(x0[i], g.convention), g.N[0], r);
-            uint32_t k = (uint32_t)(c / g.B[0]);
+            int b = c / g.B[0];
+            uint32_t k = (uint32_t)b;
+            int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;
             if (g.D > 1) {
                 c = point_to_cell0<T>(fold_point<T>(x1[i], g.convention), g.N[1], r);
-                k += (uint32_t)(c / g.B[1]) * (uint32_t)g.nb[0];
+                b = c / g.B[1];
+                sy = (c - b * g.B[1]) >> 2;
+                k += (uint32_t)b * (uint32_t)g.nb[0];
             }
             if (g.D > 2) {
                 c = point_to_cell0<T>(fold_point<T>(x2[i], g.convention), g.N[2], r);
-                k += (uint32_t)(c / g.B[2]) * (uint32_t)(g.nb[0] * g.nb[1]);
+                b = c / g.B[2];
+                sz = (c - b * g.B[2]) >> 2;
+                k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
             }
+            // rt plans: refine by (column, z block) so that the points of a 4x4-cell column are contiguous
+            if (g.rt) k = k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz);
             key = k;
             keys[i] = key;
         }
@@ -292,6 +305,27 @@ __global__ void iota_kernel(int32_t *v, int64_t n)
     if (i < n) v[i] = (int32_t)i;
 }
 
+// bin_offsets[b] = fine_offsets[b * nsub]
+__global__ void coarse_offsets_kernel(const int32_t *__restrict__ fine, int64_t nbins, int nsub, int32_t *__restrict__ out)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= nbins) out[b] = fine[b * nsub];
+}
+
+// keys[perm[k]] = bin of sorted position k (binary search in bin_offsets); introspection path only
+__global__ void coarse_keys_kernel(const int32_t *__restrict__ perm, const int32_t *__restrict__ bin_offsets, int64_t nbins,
+                                   int64_t np, uint32_t *__restrict__ keys)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= np) return;
+    int64_t lo = 0, hi = nbins;            // largest b with bin_offsets[b] <= k
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (bin_offsets[mid] <= (int32_t)k) lo = mid; else hi = mid;
+    }
+    keys[perm[k]] = (uint32_t)lo;
+}
+
 static int ensure_capacity(Plan &p, int64_t np)
 {
     if (np <= p.cap) return NUFFT_SUCCESS;
@@ -321,14 +355,16 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     BinGeom bg;
     bg.D = p.D;
     bg.convention = p.opts.point_convention;
-    for (int d = 0; d < 3; ++d) { bg.N[d] = g.N[d]; bg.B[d] = g.B[d]; bg.nb[d] = g.nb[d]; }
+    for (int d = 0; d < 3; ++d) { bg.N[d] = g.N[d]; bg.B[d] = g.B[d]; bg.nb[d] = g.nb[d]; bg.sub[d] = g.sub[d]; }
+    bg.rt = g.rt;
+    bg.nsub = g.nsub;
     const T *x0 = (const T *)x[0];
     const T *x1 = p.D > 1 ? (const T *)x[1] : nullptr;
     const T *x2 = p.D > 2 ? (const T *)x[2] : nullptr;
     cudaStream_t st = p.stream;
 
-    uint32_t *bin_count = (uint32_t *)p.d_bin_offsets;
-    CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
+    uint32_t *bin_count = (uint32_t *)p.d_fine_offsets;
+    CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins * g.nsub + 1) * sizeof(uint32_t), st));
     if (np > 0) {
         const int grid = (int)std::min<int64_t>(cdiv(np, 256), 148 * 16);
         bin_keys_kernel<T><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count);
@@ -339,47 +375,68 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     return NUFFT_SUCCESS;
 }
 
+// stable LSD radix sort of (key, index) pairs restricted to `bits` key bits; the first pass generates the
+// indices.  keys ping-pong between k0/k1 (both clobbered), values between va/vb; *result = final values.
+static int radix_sort_pairs(Plan &p, uint32_t *k0, uint32_t *k1, int32_t *va, int32_t *vb, int64_t np, int bits,
+                            int32_t **result)
+{
+    cudaStream_t st = p.stream;
+    const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+    const int nblk = (int)cdiv(np, SORT_TILE);
+    const size_t hneed = (size_t)nblk * RADIX;
+    if (hneed > p.hist_cap) {
+        if (p.d_hist) cudaFree(p.d_hist);
+        p.hist_cap = hneed + hneed / 8;
+        CUDA_TRY(cudaMalloc(&p.d_hist, p.hist_cap * sizeof(uint32_t)));
+    }
+    uint32_t *kin = k0, *kout = k1;
+    int32_t *vin = vb, *vout = va;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = pass * RADIX_BITS;
+        const bool first = pass == 0, last = pass == passes - 1;
+        radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(kin, np, shift, p.d_hist, nblk);
+        NUFFT_COUNT_LAUNCH();
+        NUFFT_TRY(scan_u32(p, p.d_hist, (int64_t)hneed, false));
+        if (first && last) radix_scatter_kernel<true, true><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
+        else if (first) radix_scatter_kernel<true, false><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
+        else if (last) radix_scatter_kernel<false, true><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
+        else radix_scatter_kernel<false, false><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
+        NUFFT_COUNT_LAUNCH();
+        std::swap(kin, kout);
+        *result = vout;
+        std::swap(vin, vout);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return NUFFT_SUCCESS;
+}
+
 template <typename T> static int run_set_points(Plan &p, int64_t np, const void *const x[])
 {
     NUFFT_TRY(ensure_capacity(p, np));
     NUFFT_TRY(set_points_impl<T>(p, np, x));
     cudaStream_t st = p.stream;
     const int64_t nb1 = p.nbins + 1;
-    NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_bin_offsets, nb1, true));
+    const int64_t nfine1 = p.nbins * p.geom.nsub + 1;
+    NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_fine_offsets, nfine1, true));
+    if (p.geom.nsub > 1) {
+        coarse_offsets_kernel<<<(unsigned)cdiv(nb1, 256), 256, 0, st>>>(p.d_fine_offsets, p.nbins, p.geom.nsub, p.d_bin_offsets);
+        NUFFT_COUNT_LAUNCH();
+    }
+    p.perm_coarse_ptr = nullptr;
 
     // stable LSD radix sort of (key, index)
-    const int passes = (p.nbins > 1 && np > 0) ? (p.key_bits + RADIX_BITS - 1) / RADIX_BITS : 0;
-    int cur = 0;
-    if (passes == 0) {
+    if (p.nbins * p.geom.nsub <= 1 || np == 0) {
         if (np > 0) {
             iota_kernel<<<(unsigned)cdiv(np, 256), 256, 0, st>>>(p.d_vals[0], np);
             NUFFT_COUNT_LAUNCH();
         }
         p.d_perm = p.d_vals[0];
+        p.sort_cur = 0;
     } else {
-        const int nblk = (int)cdiv(np, SORT_TILE);
-        const size_t hneed = (size_t)nblk * RADIX;
-        if (hneed > p.hist_cap) {
-            if (p.d_hist) cudaFree(p.d_hist);
-            p.hist_cap = hneed + hneed / 8;
-            CUDA_TRY(cudaMalloc(&p.d_hist, p.hist_cap * sizeof(uint32_t)));
-        }
-        for (int pass = 0; pass < passes; ++pass) {
-            const int shift = pass * RADIX_BITS;
-            const bool first = pass == 0, last = pass == passes - 1;
-            radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], np, shift, p.d_hist, nblk);
-            NUFFT_COUNT_LAUNCH();
-            NUFFT_TRY(scan_u32(p, p.d_hist, (int64_t)hneed, false));
-            uint32_t *ko = p.d_keys[cur ^ 1];
-            int32_t *vo = p.d_vals[cur ^ 1];
-            if (first && last) radix_scatter_kernel<true, true><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
-            else if (first) radix_scatter_kernel<true, false><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
-            else if (last) radix_scatter_kernel<false, true><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
-            else radix_scatter_kernel<false, false><<<nblk, SORT_THREADS, 0, st>>>(p.d_keys[cur], p.d_vals[cur], np, shift, p.d_hist, nblk, ko, vo);
-            NUFFT_COUNT_LAUNCH();
-            cur ^= 1;
-        }
-        p.d_perm = p.d_vals[cur];
+        int32_t *res = nullptr;
+        NUFFT_TRY(radix_sort_pairs(p, p.d_keys[0], p.d_keys[1], p.d_vals[1], p.d_vals[0], np, p.key_bits, &res));
+        p.d_perm = res;
+        p.sort_cur = (res == p.d_vals[0]) ? 0 : 1;
     }
     if (np > 0) {
         gather_points_kernel<T><<<(unsigned)cdiv(np, 256), 256, 0, st>>>(
@@ -401,6 +458,31 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
     item_table_kernel<<<(unsigned)cdiv(p.nbins, 256), 256, 0, st>>>(p.d_item_start, p.nbins, p.d_item_table);
     NUFFT_COUNT_LAUNCH();
     CUDA_TRY(cudaGetLastError());
+    return NUFFT_SUCCESS;
+}
+
+// rt plans order the points by (bin, sub-bin); the reference-order permutation (stable by bin only, what
+// BlockDataGPU.pointperm holds after the 1-thread counting sort, src/blocking/cpu.jl:73-111) is rebuilt on demand:
+// bin of every ORIGINAL index (scatter through the fine permutation), then the same stable radix sort on the bin bits.
+int binning_coarse_perm(Plan &p, const int32_t **perm)
+{
+    if (p.geom.nsub <= 1 || p.Np <= 0 || p.nbins <= 1) { *perm = p.d_perm; return NUFFT_SUCCESS; }
+    if (p.perm_coarse_ptr) { *perm = p.perm_coarse_ptr; return NUFFT_SUCCESS; }
+    const int64_t np = p.Np;
+    if (np > p.perm_coarse_cap) {
+        if (p.d_perm_coarse) cudaFree(p.d_perm_coarse);
+        p.perm_coarse_cap = 0;
+        CUDA_TRY(cudaMalloc(&p.d_perm_coarse, (size_t)p.cap * sizeof(int32_t)));
+        p.perm_coarse_cap = p.cap;
+    }
+    coarse_keys_kernel<<<(unsigned)cdiv(np, 256), 256, 0, p.stream>>>(p.d_perm, p.d_bin_offsets, p.nbins, np, p.d_keys[0]);
+    NUFFT_COUNT_LAUNCH();
+    int bits = 1;
+    while (((int64_t)1 << bits) < p.nbins) ++bits;
+    int32_t *res = nullptr;
+    NUFFT_TRY(radix_sort_pairs(p, p.d_keys[0], p.d_keys[1], p.d_perm_coarse, p.d_vals[p.sort_cur ^ 1], np, bits, &res));
+    p.perm_coarse_ptr = res;
+    *perm = res;
     return NUFFT_SUCCESS;
 }
 

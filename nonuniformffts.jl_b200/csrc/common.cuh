@@ -122,6 +122,11 @@ struct TileGeom {
     int tile_cells;  // allocated cells per tile
     int chunk;       // max points per work item
     int batch;       // points per evaluation batch (shared-memory staging)
+    // register-tile fast path (rt_spread.cuh / rt_interp.cuh; D = 3, M = 4, Float32): bins are refined into
+    // sub-bins of 4 x 4 x 4 cells; the sort key is bin * nsub + ((cy * sub[0] + cx) * sub[2] + cz)
+    int rt;          // 1 when the fast path is active
+    int sub[3];      // sub-bins per bin along each dimension (1 when !rt)
+    int nsub;        // sub[0] * sub[1] * sub[2]
 };
 
 // ---- the plan ------------------------------------------------------------------------------------
@@ -172,6 +177,11 @@ struct Plan {
     int32_t *d_perm = nullptr;       // alias into d_vals
     void *d_xs[3] = {nullptr, nullptr, nullptr};       // sorted, folded coordinates (T)
     int32_t *d_bin_offsets = nullptr;                  // nbins + 1
+    int32_t *d_fine_offsets = nullptr;                 // nbins * nsub + 1 (alias of d_bin_offsets when nsub == 1)
+    int32_t *d_perm_coarse = nullptr;                  // rt plans: bin-stable permutation, built on demand (introspection)
+    int64_t perm_coarse_cap = 0;
+    const int32_t *perm_coarse_ptr = nullptr;          // valid result of the last on-demand build (reset by set_points)
+    int sort_cur = 0;                                  // which of d_vals[] holds the permutation
     uint32_t *d_hist = nullptr;      // radix histograms
     size_t hist_cap = 0;
     uint32_t *d_scan_tmp = nullptr;
@@ -198,6 +208,9 @@ static inline int record_size(int D, int M)
     return D == 1 ? wslot : (D == 2 ? 2 * wslot : 2 * wslot + yslot);
 }
 
+// floats per point record of the register-tile kernels (rt_common.cuh)
+constexpr int RT_REC_F = 52;
+
 // kernel-launch helper: ceil-div
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -212,6 +225,7 @@ int deconv_type2_run(Plan &p, const void *const uhat[], const nufft_callbacks *c
 int fft_forward(Plan &p);
 int fft_backward(Plan &p);
 int scan_u32(Plan &p, uint32_t *data, int64_t n, bool inclusive);          // binning.cu (in place prefix sum)
+int binning_coarse_perm(Plan &p, const int32_t **perm);                    // binning.cu (rt plans: reference-order permutation)
 
 template <typename T> KernelParams<T> make_kernel_params(const Plan &p)
 {

@@ -1,7 +1,9 @@
 // interp_inst.cu — instantiates the K-interp kernels for one (T, CPLX) pair.
 // Compiled four times: -DINST_T=float|double -DINST_CPLX=0|1.
 #include <algorithm>
+#include <type_traits>
 #include "interp.cuh"
+#include "rt_interp.cuh"
 
 #ifndef INST_T
 #define INST_T float
@@ -29,6 +31,23 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
         MutPtrPack pack{};
         for (int c = 0; c < cn; ++c) pack.p[c] = vp[c0 + c];
         const Cell *us = (const Cell *)p.d_us + (int64_t)c0 * p.ncells;
+        if constexpr (std::is_same<T, float>::value && D == 3 && M == 4) {
+            if (p.geom.rt && p.method == NUFFT_METHOD_SHARED_MEMORY) {
+                auto kern = rt::rt_interp_kernel<CPLX>;
+                const size_t smem = rt::interp_smem_bytes(p.geom, p.cs_stride, sizeof(Cell));
+                const int nthreads = 32 * rt::INTERP_NW;
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int occ = 0, nsm = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem));
+                CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+                if (occ < 1) { set_error("rt_interp_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
+                SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
+                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
+                kern<<<nsm * occ, nthreads, smem, st>>>(kp, p.geom, a, p.d_fine_offsets, xs0, xs1, xs2, pack, cn, us, p.ncells, prefactor, nuw);
+                NUFFT_COUNT_LAUNCH();
+                continue;
+            }
+        }
         if (p.method == NUFFT_METHOD_GLOBAL_MEMORY) {
             interp_gm_kernel<T, CPLX, D, M><<<(unsigned)cdiv(np, 128), 128, 0, st>>>(
                 kp, np, xs0, xs1, xs2, p.d_perm, pack, cn, us, p.ncells, prefactor, nuw);

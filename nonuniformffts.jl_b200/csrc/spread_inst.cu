@@ -1,7 +1,9 @@
 // spread_inst.cu — instantiates the K-spread kernels for one (T, CPLX) pair.
 // Compiled four times: -DINST_T=float|double -DINST_CPLX=0|1 (keeps each nvcc job short).
 #include <algorithm>
+#include <type_traits>
 #include "spread.cuh"
+#include "rt_spread.cuh"
 
 #ifndef INST_T
 #define INST_T float
@@ -27,6 +29,24 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
         PtrPack pack{};
         for (int c = 0; c < cn; ++c) pack.p[c] = vp[c0 + c];
         Cell *us = (Cell *)p.d_us + (int64_t)c0 * p.ncells;
+        if constexpr (std::is_same<T, float>::value && D == 3 && M == 4) {
+            if (p.geom.rt && p.method == NUFFT_METHOD_SHARED_MEMORY) {
+                constexpr int NPROD = 1;
+                auto kern = rt::rt_spread_kernel<CPLX, NPROD>;
+                const size_t smem = rt::spread_smem_bytes(p.geom, p.cs_stride, sizeof(Cell));
+                const int nthreads = 32 * (rt::SPREAD_NCONS + NPROD);
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int occ = 0, nsm = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem));
+                CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+                if (occ < 1) { set_error("rt_spread_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
+                SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
+                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
+                kern<<<nsm * occ, nthreads, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, nuw);
+                NUFFT_COUNT_LAUNCH();
+                continue;
+            }
+        }
         if (p.method == NUFFT_METHOD_GLOBAL_MEMORY) {
             spread_gm_kernel<T, CPLX, D, M><<<(unsigned)cdiv(np, 128), 128, 0, st>>>(
                 kp, np, xs0, xs1, xs2, p.d_perm, pack, cn, us, p.ncells, nuw);

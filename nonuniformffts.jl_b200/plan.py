@@ -426,6 +426,18 @@ class PlanNUFFT:
         o = _tensor_from_ptr(off.value, (nb.value + 1,), torch.int32, self.device, self)
         return p, o, tuple(int(bd[d]) for d in range(self._ndims))
 
+    def binning_fine(self):
+        """(perm, fine_offsets, sub_dims): the (bin, sub-bin) order the kernels use (register-tile fast path);
+        identical to `binning()` with sub_dims == (1, 1, 1) on other plans."""
+        perm, off = C.c_void_p(), C.c_void_p()
+        nf = C.c_int64()
+        sd = (C.c_int64 * 3)()
+        _check(self._lib.nufft_get_binning_fine(self._h, C.byref(perm), C.byref(off), C.byref(nf), sd))
+        p = _tensor_from_ptr(perm.value, (self.Np,), torch.int32, self.device, self) if self.Np else \
+            torch.empty(0, dtype=torch.int32, device=self.device)
+        o = _tensor_from_ptr(off.value, (nf.value + 1,), torch.int32, self.device, self)
+        return p, o, tuple(int(sd[d]) for d in range(3))
+
     def kernel_info(self, d: int = 0):
         import numpy as np
         shape, dx = C.c_double(), C.c_double()
