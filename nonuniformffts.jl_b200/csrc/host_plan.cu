@@ -280,7 +280,10 @@ static bool choose_geometry(Plan &p)
     // bins are multiples of the 4^3-cell sub-bin, at most 16 cells along z (6 register planes per consumer warp)
     {
         bool rt = D == 3 && M == 4 && !p.f64 && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY;
-        if (const char *e = getenv("NUFFT_B200_RT")) rt = rt && atoi(e) != 0;
+        {   // opt-in until it beats the shared-memory-tile kernels (NUFFT_B200_RT=1)
+            const char *e = getenv("NUFFT_B200_RT");
+            rt = rt && e && atoi(e) != 0;
+        }
         int Br[3] = {16, 16, 16};
         if (const char *e = getenv("NUFFT_B200_RT_BIN")) {     // tuning knob: "bx,by,bz"
             int a = 0, b = 0, c = 0;

@@ -29,7 +29,7 @@ constexpr int NPL = 6;             // z planes per consumer warp in spreading (t
 //   [16..39]  wyT[6]    float4 rows of wy_pad: row0 = (p0,p3,p6,p9) row1 = (p1,p4,p7,p10) row2 = (p2,p5,p8,0)
 //                        row3..5 = (p2,p5,p8, p2|p5|p8)   (lanes 22..24: 4th slot at x = 10)
 //   [40..50]  wx_pad[11]
-//   [51]      meta      column x | column y << 8 | local z start << 16
+//   [51]      meta      bytes: column x, column y, local z start, 0
 // 52 floats = 208 bytes: consecutive records start 80 banks apart -> 16-byte stores of 8 threads are conflict-free.
 constexpr int REC_F = RT_REC_F;
 constexpr int OFF_S = 0, OFF_WY = 16, OFF_WX = 40, OFF_META = 51;
@@ -71,8 +71,8 @@ __device__ __forceinline__ void pad_shift(const float (&w)[W], int o, float (&p)
     }
 }
 
-// store wy_pad as the six float4 rows and wx_pad + meta (thread-per-point producers)
-__device__ __forceinline__ void store_xy(float *rec, const float (&px)[P], const float (&py)[P], int meta)
+// store wy_pad as the six float4 rows of the record
+__device__ __forceinline__ void store_y(float *rec, const float (&py)[P])
 {
     float4 *r = reinterpret_cast<float4 *>(rec + OFF_WY);
     r[0] = make_float4(py[0], py[3], py[6], py[9]);
@@ -81,10 +81,6 @@ __device__ __forceinline__ void store_xy(float *rec, const float (&px)[P], const
     r[3] = make_float4(py[2], py[5], py[8], py[2]);
     r[4] = make_float4(py[2], py[5], py[8], py[5]);
     r[5] = make_float4(py[2], py[5], py[8], py[8]);
-    float4 *q = reinterpret_cast<float4 *>(rec + OFF_WX);
-    q[0] = make_float4(px[0], px[1], px[2], px[3]);
-    q[1] = make_float4(px[4], px[5], px[6], px[7]);
-    q[2] = make_float4(px[8], px[9], px[10], __int_as_float(meta));
 }
 
 }  // namespace rt

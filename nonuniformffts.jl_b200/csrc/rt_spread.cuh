@@ -3,9 +3,12 @@
 // Replaces src/spreading/gpu.jl:237-434 for this configuration class (same sums, different order).
 //
 // CTA = 4 consumer warps + NPROD producer warps, persistent, pulling (bin, chunk) work items from a device counter.
-//   producers : one thread per point — kernel values (eval_kernel_values, same polynomials as every other path),
-//               zero-padded to the column footprint, the value pre-multiplied into the z weights — written as a
-//               208-byte record, double buffered (one CTA barrier per 32-point batch);
+//   producers : three warps, one per DIMENSION, one thread per point of the 32-point batch — kernel values
+//               (eval_kernel_values, same polynomials as every other path) zero-padded to the column footprint (x, y)
+//               or pre-multiplied by the point's value (z) — written as a 208-byte record, double buffered (one CTA
+//               barrier per batch).  Coordinates / permutation / values of the following batches are prefetched
+//               into registers (the value gather vp[perm[k]] is two dependent loads), so the evaluation never
+//               waits on global memory;
 //   consumers : warp w owns the tile planes z = w (mod 4).  A point's 8 planes meet every class exactly twice, so
 //               every consumer does the same work for every point (no imbalance, nothing shared between warps, no
 //               shared-memory atomics).  Per point and warp: 4 shared-memory loads, 4 FMUL, 16 FFMA into the
@@ -22,17 +25,17 @@ namespace nufft {
 namespace rt {
 
 constexpr int SPREAD_NCONS = 4;
+constexpr int SPREAD_NPROD = 3;        // producer warps: one per dimension
 
-template <bool CPLX, int NPROD>
-__global__ void __launch_bounds__(32 * (SPREAD_NCONS + NPROD), 2)
+template <bool CPLX>
+__global__ void __launch_bounds__(32 * (SPREAD_NCONS + SPREAD_NPROD), 2)
 rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__restrict__ xs0, const float *__restrict__ xs1,
                  const float *__restrict__ xs2, PtrPack vp, int C, typename CellOf<float, CPLX>::type *__restrict__ us,
                  int64_t ncells, const float *__restrict__ nu_weights)
 {
     using Cell = typename CellOf<float, CPLX>::type;
-    constexpr int NWARP = SPREAD_NCONS + NPROD;
+    constexpr int NWARP = SPREAD_NCONS + SPREAD_NPROD;
     constexpr int NT = 32 * NWARP;
-    constexpr int NPT = 32 * NPROD;
     constexpr int VEC = FlushVec<Cell>::VEC;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -44,7 +47,8 @@ rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool consumer = warp < SPREAD_NCONS;
-    const int ptid = tid - 32 * SPREAD_NCONS;
+    const int role = warp - SPREAD_NCONS;                              // producers: dimension evaluated by this warp
+    const float *xs_r = role == 0 ? xs0 : (role == 1 ? xs1 : xs2);
     const int Tx = g.T[0], Ty = g.T[1], Tz = g.T[2], Sx = g.S[0], S2 = g.S[2];
     const int total_items = a.item_start[a.nbins];
 
@@ -88,31 +92,68 @@ rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
         const int nbatches = (k1 - k0 + g.batch - 1) / g.batch;
 
         for (int c = 0; c < C; ++c) {
-            // ---- producer: one thread per point ------------------------------------------------------------
+            // ---- producers: warp `role` evaluates dimension `role` of the batch, one thread per point ------------
+            // register prefetch: xq = coordinate of this lane's point in the NEXT batch to produce, vq = its value
+            // (z warp), nq = permutation entry of the batch after that
+            float xq = 0.f;
+            Cell vq = cell_zero((Cell *)nullptr);
+            int32_t nq = 0;
+            auto load_v = [&](int32_t n) -> Cell {
+                Cell v = load_value<float, CPLX>(vp.p[c], n);
+                if (nu_weights) v = cmul(v, nu_weights[n]);
+                return v;
+            };
+            if (!consumer) {
+                const int k = k0 + lane;
+                if (k < k1) xq = xs_r[k];
+                if (role == 2) {
+                    if (k < k1) vq = load_v(a.perm[k]);
+                    if (k + 32 < k1) nq = a.perm[k + 32];
+                }
+            }
             auto produce = [&](int bi) {
-                const int kb = k0 + bi * g.batch;
+                const int kb = k0 + bi * g.batch;          // g.batch == 32
                 const int nb = min(g.batch, k1 - kb);
-                float *rec_b = rec_s + (bi & 1) * g.batch * REC_F;
-                for (int p = ptid; p < nb; p += NPT) {
-                    const int32_t n = a.perm[kb + p];
-                    const float x0 = xs0[kb + p], x1 = xs1[kb + p], x2 = xs2[kb + p];
-                    Cell v = load_value<float, CPLX>(vp.p[c], n);
-                    if (nu_weights) v = cmul(v, nu_weights[n]);
-                    float *r = rec_b + p * REC_F;
-                    float w[W], px[P], py[P];
-                    const int tx = eval_kernel_values<float, M>(kp, cs_s, 0, x0, w) - org0;
-                    pad_shift(w, tx & 3, px);
-                    const int ty = eval_kernel_values<float, M>(kp, cs_s + kp.cs_stride, 1, x1, w) - org1;
-                    pad_shift(w, ty & 3, py);
-                    const int tz = eval_kernel_values<float, M>(kp, cs_s + 2 * kp.cs_stride, 2, x2, w) - org2;
-                    store_xy(r, px, py, (tx >> 2) | ((ty >> 2) << 8) | (tz << 16));
-                    // z weights by residue class of the tile plane: planes tz + j, j = 0..7; class (tz + j) & 3
-                    float vr, vi;
-                    if constexpr (CPLX) { vr = v.x; vi = v.y; } else { vr = v; vi = 0.f; }
-                    float4 *s = reinterpret_cast<float4 *>(r + OFF_S);
+                float *r = rec_s + ((bi & 1) * g.batch + lane) * REC_F;
+                const float x = xq;
+                const Cell v = vq;
+                {   // issue the loads of the following batches before evaluating this one
+                    const int kn = kb + 32 + lane;
+                    if (kn < k1) {
+                        xq = xs_r[kn];
+                        if (role == 2) vq = load_v(nq);
+                    }
+                    if (role == 2 && kn + 32 < k1) nq = a.perm[kn + 32];
+                }
+                if (lane < nb) {
+                    float w[W], pw[P];
+                    unsigned char *mb = reinterpret_cast<unsigned char *>(r + OFF_META);
+                    if (role == 0) {
+                        const int tx = eval_kernel_values<float, M>(kp, cs_s, 0, x, w) - org0;
+                        pad_shift(w, tx & 3, pw);
+                        float4 *q = reinterpret_cast<float4 *>(r + OFF_WX);
+                        q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                        q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+                        *reinterpret_cast<float2 *>(r + OFF_WX + 8) = make_float2(pw[8], pw[9]);
+                        r[OFF_WX + 10] = pw[10];
+                        mb[0] = (unsigned char)(tx >> 2);
+                    } else if (role == 1) {
+                        const int ty = eval_kernel_values<float, M>(kp, cs_s + kp.cs_stride, 1, x, w) - org1;
+                        pad_shift(w, ty & 3, pw);
+                        store_y(r, pw);
+                        mb[1] = (unsigned char)(ty >> 2);
+                    } else {
+                        const int tz = eval_kernel_values<float, M>(kp, cs_s + 2 * kp.cs_stride, 2, x, w) - org2;
+                        // z weights by residue class of the tile plane: planes tz + j, j = 0..7; class (tz + j) & 3
+                        float vr, vi;
+                        if constexpr (CPLX) { vr = v.x; vi = v.y; } else { vr = v; vi = 0.f; }
+                        float4 *s4 = reinterpret_cast<float4 *>(r + OFF_S);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        s[(tz + j) & 3] = make_float4(vr * w[j], vi * w[j], vr * w[j + 4], vi * w[j + 4]);
+                        for (int j = 0; j < 4; ++j)
+                            s4[(tz + j) & 3] = make_float4(vr * w[j], vi * w[j], vr * w[j + 4], vi * w[j + 4]);
+                        mb[2] = (unsigned char)tz;
+                        mb[3] = 0;
+                    }
                 }
             };
             // ---- consumer: add the register tile of column `col` to the shared-memory tile, clear it --------
@@ -158,7 +199,7 @@ rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
                         const float wx_n = rn[OFF_WX + ls.x], wx3_n = rn[OFF_WX + ls.x3];
                         const int meta_n = __float_as_int(rn[OFF_META]);
 
-                        const int col = meta & 0xffff, tz = meta >> 16;
+                        const int col = meta & 0xffff, tz = (meta >> 16) & 0xff;
                         if (col != cur_col) {
                             if (cur_col >= 0) flush_col(cur_col);
                             cur_col = col;

@@ -31,10 +31,9 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
         Cell *us = (Cell *)p.d_us + (int64_t)c0 * p.ncells;
         if constexpr (std::is_same<T, float>::value && D == 3 && M == 4) {
             if (p.geom.rt && p.method == NUFFT_METHOD_SHARED_MEMORY) {
-                constexpr int NPROD = 1;
-                auto kern = rt::rt_spread_kernel<CPLX, NPROD>;
+                auto kern = rt::rt_spread_kernel<CPLX>;
                 const size_t smem = rt::spread_smem_bytes(p.geom, p.cs_stride, sizeof(Cell));
-                const int nthreads = 32 * (rt::SPREAD_NCONS + NPROD);
+                const int nthreads = 32 * (rt::SPREAD_NCONS + rt::SPREAD_NPROD);
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 0, nsm = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem));
