@@ -183,8 +183,8 @@ int nufft_get_binning_fine(nufft_plan h, const int32_t **perm, const int32_t **f
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (p.Np < 0) { set_error("set_points has not been called"); return NUFFT_ERR_STATE; }
     if (perm) *perm = p.d_perm;
-    if (fine_offsets) *fine_offsets = p.d_fine_offsets;
-    if (nfine) *nfine = p.nbins * p.geom.nsub;
+    if (fine_offsets) *fine_offsets = p.geom.nsub > 1 ? nullptr : p.d_bin_offsets;   // sub-bin offsets are not materialised
+    if (nfine) *nfine = p.geom.nsub > 1 ? 0 : p.nbins;
     if (sub_dims) for (int d = 0; d < 3; ++d) sub_dims[d] = p.geom.sub[d];
     return NUFFT_SUCCESS;
 }

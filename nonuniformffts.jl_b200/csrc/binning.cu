@@ -57,7 +57,7 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
             int c = point_to_cell0<T>(fold_point<T>(x0[i], g.convention), g.N[0], r);
             int b = c / g.B[0];
             uint32_t k = (uint32_t)b;
-            int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;
+            int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // rt: 4-cell columns in x, y; single cells in z
             if (g.D > 1) {
                 c = point_to_cell0<T>(fold_point<T>(x1[i], g.convention), g.N[1], r);
                 b = c / g.B[1];
@@ -67,15 +67,15 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
             if (g.D > 2) {
                 c = point_to_cell0<T>(fold_point<T>(x2[i], g.convention), g.N[2], r);
                 b = c / g.B[2];
-                sz = (c - b * g.B[2]) >> 2;
+                sz = c - b * g.B[2];
                 k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
             }
-            // rt plans: refine by (column, z block) so that the points of a 4x4-cell column are contiguous
-            if (g.rt) k = k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz);
+            // rt plans: refine by (column, z cell) so that the points of a 4x4-cell column are contiguous and
+            // ordered along z; the histogram stays per bin
             key = k;
-            keys[i] = key;
+            keys[i] = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
         }
-        // warp-aggregated histogram: one atomic per distinct key in the warp (clustered inputs)
+        // warp-aggregated histogram: one atomic per distinct bin in the warp (clustered inputs)
         const unsigned active = __ballot_sync(0xffffffffu, valid);
         if (valid) {
             const unsigned peers = __match_any_sync(active, key);
@@ -305,13 +305,6 @@ __global__ void iota_kernel(int32_t *v, int64_t n)
     if (i < n) v[i] = (int32_t)i;
 }
 
-// bin_offsets[b] = fine_offsets[b * nsub]
-__global__ void coarse_offsets_kernel(const int32_t *__restrict__ fine, int64_t nbins, int nsub, int32_t *__restrict__ out)
-{
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b <= nbins) out[b] = fine[b * nsub];
-}
-
 // keys[perm[k]] = bin of sorted position k (binary search in bin_offsets); introspection path only
 __global__ void coarse_keys_kernel(const int32_t *__restrict__ perm, const int32_t *__restrict__ bin_offsets, int64_t nbins,
                                    int64_t np, uint32_t *__restrict__ keys)
@@ -363,8 +356,8 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     const T *x2 = p.D > 2 ? (const T *)x[2] : nullptr;
     cudaStream_t st = p.stream;
 
-    uint32_t *bin_count = (uint32_t *)p.d_fine_offsets;
-    CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins * g.nsub + 1) * sizeof(uint32_t), st));
+    uint32_t *bin_count = (uint32_t *)p.d_bin_offsets;
+    CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
     if (np > 0) {
         const int grid = (int)std::min<int64_t>(cdiv(np, 256), 148 * 16);
         bin_keys_kernel<T><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count);
@@ -416,12 +409,7 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
     NUFFT_TRY(set_points_impl<T>(p, np, x));
     cudaStream_t st = p.stream;
     const int64_t nb1 = p.nbins + 1;
-    const int64_t nfine1 = p.nbins * p.geom.nsub + 1;
-    NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_fine_offsets, nfine1, true));
-    if (p.geom.nsub > 1) {
-        coarse_offsets_kernel<<<(unsigned)cdiv(nb1, 256), 256, 0, st>>>(p.d_fine_offsets, p.nbins, p.geom.nsub, p.d_bin_offsets);
-        NUFFT_COUNT_LAUNCH();
-    }
+    NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_bin_offsets, nb1, true));
     p.perm_coarse_ptr = nullptr;
 
     // stable LSD radix sort of (key, index)

@@ -122,8 +122,8 @@ struct TileGeom {
     int tile_cells;  // allocated cells per tile
     int chunk;       // max points per work item
     int batch;       // points per evaluation batch (shared-memory staging)
-    // register-tile fast path (rt_spread.cuh / rt_interp.cuh; D = 3, M = 4, Float32): bins are refined into
-    // sub-bins of 4 x 4 x 4 cells; the sort key is bin * nsub + ((cy * sub[0] + cx) * sub[2] + cz)
+    // register-window fast path (rt_spread.cuh / rt_interp.cuh; D = 3, M = 4, Float32): bins are refined into
+    // columns of 4 x 4 cells and single cells along z; the sort key is bin * nsub + ((cy * sub[0] + cx) * sub[2] + cz)
     int rt;          // 1 when the fast path is active
     int sub[3];      // sub-bins per bin along each dimension (1 when !rt)
     int nsub;        // sub[0] * sub[1] * sub[2]
@@ -177,7 +177,6 @@ struct Plan {
     int32_t *d_perm = nullptr;       // alias into d_vals
     void *d_xs[3] = {nullptr, nullptr, nullptr};       // sorted, folded coordinates (T)
     int32_t *d_bin_offsets = nullptr;                  // nbins + 1
-    int32_t *d_fine_offsets = nullptr;                 // nbins * nsub + 1 (alias of d_bin_offsets when nsub == 1)
     int32_t *d_perm_coarse = nullptr;                  // rt plans: bin-stable permutation, built on demand (introspection)
     int64_t perm_coarse_cap = 0;
     const int32_t *perm_coarse_ptr = nullptr;          // valid result of the last on-demand build (reset by set_points)

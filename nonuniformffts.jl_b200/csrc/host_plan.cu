@@ -276,30 +276,28 @@ static bool choose_geometry(Plan &p)
     g.sub[0] = g.sub[1] = g.sub[2] = 1;
     g.nsub = 1;
 
-    // ---- register-tile fast path (rt_spread.cuh / rt_interp.cuh): D = 3, M = 4, Float32 ------------------------
-    // bins are multiples of the 4^3-cell sub-bin, at most 16 cells along z (6 register planes per consumer warp)
+    // ---- register-window fast path (rt_spread.cuh / rt_interp.cuh): D = 3, M = 4, Float32 ----------------------
+    // bins of 16 x 16 cells in (x, y) (4 x 4 columns of 4 x 4 cells) and Bz cells along z, Bz chosen so that two CTAs
+    // (tile + point records) are resident per SM; the sort key is refined by (column, z cell)
     {
-        bool rt = D == 3 && M == 4 && !p.f64 && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY;
+        bool rt = D == 3 && M == 4 && !p.f64 && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
         {   // opt-in until it beats the shared-memory-tile kernels (NUFFT_B200_RT=1)
             const char *e = getenv("NUFFT_B200_RT");
             rt = rt && e && atoi(e) != 0;
         }
-        int Br[3] = {16, 16, 16};
-        if (const char *e = getenv("NUFFT_B200_RT_BIN")) {     // tuning knob: "bx,by,bz"
-            int a = 0, b = 0, c = 0;
-            if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) { Br[0] = a; Br[1] = b; Br[2] = c; }
-        }
+        int Br[3] = {16, 16, 12};
+        if (const char *e = getenv("NUFFT_B200_RT_BZ")) { const int v = atoi(e); if (v >= 1 && v <= 64) Br[2] = v; }
         for (int d = 0; d < D && rt; ++d) {
-            int64_t b = user ? (p.opts.block_dims[d] > 0 ? p.opts.block_dims[d] : 16) : Br[d];
-            if (user && (b % 4 != 0)) rt = false;
-            b = std::min<int64_t>(b, bcap(d)) / 4 * 4;
-            if (b < 4 || (d == 2 && b > 16) || b > 64) rt = false;
-            Br[d] = (int)b;
+            if (d < 2 && bcap(d) < 16) rt = false;
+            Br[d] = (int)std::min<int64_t>(Br[d], bcap(d));
         }
+        auto rt_need = [&](int bz) -> size_t {
+            const size_t tile = (size_t)(16 + W - 1) * (16 + W - 1) * (bz + W - 1) * cell_bytes;
+            return tile + (size_t)4 * 32 * RT_REC_F * sizeof(float) + ((size_t)D * p.cs_stride + 4) * p.real_bytes + 256;
+        };
         if (rt) {
-            const size_t tile = (size_t)(Br[0] + W - 1) * (Br[1] + W - 1) * (Br[2] + W - 1) * cell_bytes;
-            const size_t need = tile + (size_t)2 * 32 * RT_REC_F * sizeof(float) + ((size_t)D * p.cs_stride + 4) * p.real_bytes + 256;
-            if (need > (size_t)SMEM_MAX_CTA) rt = false;
+            while (Br[2] > 4 && rt_need(Br[2]) > (size_t)(SMEM_PER_SM / 2 - 1024)) --Br[2];
+            if (rt_need(Br[2]) > (size_t)SMEM_MAX_CTA) rt = false;
         }
         if (rt) {
             g.rt = 1;
@@ -307,13 +305,12 @@ static bool choose_geometry(Plan &p)
             int64_t nbins = 1;
             for (int d = 0; d < 3; ++d) {
                 g.B[d] = Br[d]; g.T[d] = Br[d] + W - 1;
-                g.sub[d] = Br[d] / 4;
+                g.sub[d] = d < 2 ? Br[d] / 4 : Br[d];
                 g.nb[d] = (int)cdiv(p.Nos[d], Br[d]);
                 nbins *= g.nb[d];
             }
             g.nsub = g.sub[0] * g.sub[1] * g.sub[2];
             g.S[0] = g.T[0];
-            if (const char *e = getenv("NUFFT_B200_RT_PITCH")) { const int v = atoi(e); if (v >= g.T[0] && v <= g.T[0] + 16) g.S[0] = v; }
             g.S[1] = g.S[0];
             g.S[2] = g.S[0] * g.T[1];
             g.tile_cells = g.S[0] * g.T[1] * g.T[2];
@@ -502,8 +499,6 @@ int host_plan_init(Plan &p)
 
     // binning tables that depend only on the plan
     CUDA_TRY(cudaMalloc(&p.d_bin_offsets, (size_t)(p.nbins + 1) * sizeof(int32_t)));
-    if (p.geom.nsub > 1) CUDA_TRY(cudaMalloc(&p.d_fine_offsets, (size_t)(p.nbins * p.geom.nsub + 1) * sizeof(int32_t)));
-    else p.d_fine_offsets = p.d_bin_offsets;
     CUDA_TRY(cudaMalloc(&p.d_item_start, (size_t)(p.nbins + 1) * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&p.d_counters, 64 * sizeof(int32_t)));
     CUDA_TRY(cudaMemset(p.d_counters, 0, 64 * sizeof(int32_t)));
@@ -524,8 +519,6 @@ void host_plan_free(Plan &p)
     f(p.d_us); f(p.d_cs);
     for (int d = 0; d < 3; ++d) { f(p.d_phihat[d]); f(p.d_imap[d]); f(p.d_invmap[d]); f(p.d_xs[d]); }
     f(p.d_keys[0]); f(p.d_keys[1]); f(p.d_vals[0]); f(p.d_vals[1]);
-    if (p.d_fine_offsets != p.d_bin_offsets) f(p.d_fine_offsets);
-    p.d_fine_offsets = nullptr;
     f(p.d_perm_coarse);
     f(p.d_bin_offsets); f(p.d_hist); f(p.d_scan_tmp); f(p.d_item_start); f(p.d_item_table); f(p.d_counters);
     if (p.ev_ok) { for (int i = 0; i < 32; ++i) cudaEventDestroy(p.ev[i]); p.ev_ok = false; }

@@ -43,7 +43,7 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
                 if (occ < 1) { set_error("rt_interp_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
                 SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
                 CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
-                kern<<<nsm * occ, nthreads, smem, st>>>(kp, p.geom, a, p.d_fine_offsets, xs0, xs1, xs2, pack, cn, us, p.ncells, prefactor, nuw);
+                kern<<<nsm * occ, nthreads, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, prefactor, nuw);
                 NUFFT_COUNT_LAUNCH();
                 continue;
             }

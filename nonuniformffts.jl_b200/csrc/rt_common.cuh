@@ -1,14 +1,16 @@
-// rt_common.cuh — pieces shared by the register-tile spreading / interpolation kernels (rt_spread.cuh, rt_interp.cuh).
+// rt_common.cuh — pieces shared by the register-window spreading / interpolation kernels (rt_spread.cuh, rt_interp.cuh).
 //
 // Fast path for the headline configuration class: D = 3, HalfSupport(4), Float32 (real or complex data).
-// A bin (<= 16 cells along z, multiples of 4 cells) is refined into COLUMNS of 4 x 4 cells; set_points orders the
-// points by (bin, column, z block of 4 cells).  All points of a column touch the same padded (x, y) footprint of
-// P x P = 11 x 11 cells, so a warp keeps that footprint in REGISTERS — lane L owns the cells (slots)
+// A bin (multiples of 4 cells in x and y) is refined into COLUMNS of 4 x 4 cells; set_points orders the points by
+// (bin, column, z cell).  All points of a column touch the same padded (x, y) footprint of P x P = 11 x 11 cells, so a
+// warp keeps that footprint in REGISTERS — lane L owns the cells (slots)
 //       (x = L % 11, y = L / 11 + 3k), k = 0..3        [121 cells = 32 lanes x 4 slots - 7]
-// (the three cells (10, 2), (10, 5), (10, 8) that this map misses are the 4th slot of lanes 22, 23, 24) — for a
-// stack of z planes, and shared memory is touched once per column instead of once per point:
-//   spreading      accumulate points into registers, read-modify-write the tile when the column changes;
-//   interpolation  load the column's cells once, then every point is a register dot product.
+// (the three cells (10, 2), (10, 5), (10, 8) that this map misses are the 4th slot of lanes 22, 23, 24) — for the two
+// z planes of its residue class (z mod 4) that the current point touches.  Inside a column z only grows, so the plane
+// window slides monotonically and shared memory is touched once per (column, plane) instead of once per point:
+//   spreading      accumulate points into registers (packed FFMA2), read-modify-write a tile plane when the window
+//                  moves past it;
+//   interpolation  load a plane's cells when the window reaches it, then every point is a register dot product.
 // The per-point weights are zero-padded to the footprint: wx_pad[x], wy_pad[y] (x, y in 0..10) vanish outside the
 // point's 8 x 8 support, so every lane applies the same code to its fixed slots.
 #pragma once
@@ -21,18 +23,67 @@ constexpr int M = 4;
 constexpr int W = 8;
 constexpr int SB = 4;              // sub-bin edge (cells)
 constexpr int P = SB + W - 1;      // padded footprint edge = 11
-constexpr int NPL = 6;             // z planes per consumer warp in spreading (tile height <= 24)
+constexpr int BATCH = 32;          // points per evaluation batch (one thread per point)
+
+// packed 2 x f32 arithmetic (sm_100a FFMA2 / FMUL2); pk2(w, w) operands fold into the .F32 broadcast form
+using u64 = unsigned long long;
+__device__ __forceinline__ u64 pk2(float a, float b)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float2 unpk2(u64 v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 fmul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// in-place register updates (read-write asm operands keep a large register state where it is: the compiler would
+// otherwise copy every accumulator around the rarely taken window-move branches)
+__device__ __forceinline__ void zero_inplace(u64 &v) { asm volatile("mov.b64 %0, 0;" : "+l"(v)); }
+__device__ __forceinline__ void lds64_inplace(u64 &v, const void *p)
+{
+    asm volatile("ld.shared.b64 %0, [%1];" : "+l"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+}
+__device__ __forceinline__ void lds32x2_inplace(u64 &v, const void *p0, const void *p1)   // v = (*(float *)p0, *(float *)p1)
+{
+    asm volatile("{\n\t.reg .b32 lo, hi;\n\tld.shared.b32 lo, [%1];\n\tld.shared.b32 hi, [%2];\n\tmov.b64 %0, {lo, hi};\n\t}"
+                 : "+l"(v)
+                 : "r"((unsigned)__cvta_generic_to_shared(p0)), "r"((unsigned)__cvta_generic_to_shared(p1))
+                 : "memory");
+}
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 
 // Per-point record in shared memory (floats):
-//   [ 0..15]  s[4]      float4 per z residue class r = tile z mod 4 (spreading: value x the two wz of the class;
-//                        interpolation: [0..7] = wz[0..7])
+//   [ 0..15]  s[4]      float4 per z residue class r = tile z mod 4.  Spreading: value x the two wz of the class,
+//                        (even plane re, im, odd plane re, im) [real data: (even, odd, -, -)], even / odd = parity of
+//                        the plane index q = z >> 2 inside the class; interpolation: (wz even, wz odd, -, -)
 //   [16..39]  wyT[6]    float4 rows of wy_pad: row0 = (p0,p3,p6,p9) row1 = (p1,p4,p7,p10) row2 = (p2,p5,p8,0)
 //                        row3..5 = (p2,p5,p8, p2|p5|p8)   (lanes 22..24: 4th slot at x = 10)
-//   [40..50]  wx_pad[11]
-//   [51]      meta      bytes: column x, column y, local z start, 0
-// 52 floats = 208 bytes: consecutive records start 80 banks apart -> 16-byte stores of 8 threads are conflict-free.
+//   [40..51]  wx_pad[11], 0
+// 52 floats = 208 bytes: consecutive records start 20 banks apart -> 16-byte stores of 8 threads are conflict-free.
+// Per-point keys (separate int4 array, one int per residue class c): (column y << 12) | (column x << 8) | q_c, q_c =
+// first plane index of class c inside the point's support = ceil((tz - c) / 4), tz = z cell relative to the bin.
 constexpr int REC_F = RT_REC_F;
-constexpr int OFF_S = 0, OFF_WY = 16, OFF_WX = 40, OFF_META = 51;
+constexpr int OFF_S = 0, OFF_WY = 16, OFF_WX = 40;
 static_assert(REC_F == 52, "record layout");
 
 struct LaneSlots {

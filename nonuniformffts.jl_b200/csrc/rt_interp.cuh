@@ -1,105 +1,72 @@
-// rt_interp.cuh — K-interp, register-tile variant (3-D, HalfSupport(4), Float32).  See rt_common.cuh for the idea.
+// rt_interp.cuh — K-interp, register-window variant (3-D, HalfSupport(4), Float32).  See rt_common.cuh for the idea.
 //
 // Replaces src/interpolation/gpu.jl:211-395 for this configuration class (same sums, different order).
 //
-// Persistent CTA of NW independent warps; (bin, chunk) work items from a device counter.  The bin's padded tile is
-// staged in shared memory with cp.async, DOUBLE BUFFERED: the tile of the next work item is in flight while the
-// current one is processed.  Each warp then takes sub-bins of 4 x 4 x ZB cells (ZB = 8: a column's z blocks 2h, 2h+1;
-// set_points sorted the points by (column, z block)), loads the sub-bin's padded footprint 11 x 11 x (ZB + 7) into
-// REGISTERS once (4 slots per lane and plane), and every point of the sub-bin is a register dot product:
-//   * all 32 lanes evaluate one zero-padded kernel value each (12 for x, 12 for y, 8 for z: one Horner pass with a
-//     per-lane coefficient column) and exchange them through a per-warp scratch record;
-//   * 8 planes x (4 complex FMA + 1) per lane, selected by the local z start (switch -> static register indices);
-//   * 5-step shuffle reduction, lane 0 scatters through the permutation.
-// Shared memory is read once per sub-bin (60 LDS.64 per lane for ~16 points) instead of 16 LDS.64 per point.
+// CTA = 4 independent warps sharing one read-only tile (the bin's padded subgrid, staged with cp.async), persistent,
+// pulling (bin, chunk) work items from a device counter.  Inside an item the warps pull 32-point batches from a
+// shared-memory counter; a batch never leaves its warp (no CTA barrier between tile loads):
+//   evaluate   one thread per point: x / y kernel values zero-padded to the column footprint, z values ROTATED so that
+//              the weight of tile plane z sits at index z & 7, and the (column, z) key -> the warp's private record
+//              buffer;
+//   accumulate lane L keeps its 4 footprint cells of the 8 planes [tz, tz + 8) in registers (plane z in register set
+//              z & 7).  Points arrive ordered by (column, z): when the window moves only the new planes are loaded.
+//              Per point: 6 shared-memory loads, 36 FFMA2 (packed re/im), then the 32 lane partials of 32 consecutive
+//              points are summed by a streaming butterfly transposition (31 exchanges per 32 points) that leaves
+//              point bitrev5(L) in lane L;
+//   store      prefactor, non-uniform callback, scatter through the permutation.
 #pragma once
 #include "rt_common.cuh"
-#include "interp.cuh"
 
 namespace nufft {
 namespace rt {
 
-constexpr int INTERP_NW = 12;             // warps per CTA
-constexpr int ZB = 8;                     // z cells per register sub-bin
-constexpr int ZP = ZB + W - 1;            // register planes = 15
-constexpr int SCR_F = 48;                 // per-warp scratch record: wz[8] | wyT[6][4] | wx_pad[12] (+pad)
-constexpr int SCR_WZ = 0, SCR_WY = 8, SCR_WX = 32;
+constexpr int INTERP_NW = 4;
+constexpr int IOFF_WZ = 0, IOFF_KEY = 8;          // record: [0..7] rotated wz, [8] key, [16..39] wyT, [40..51] wx_pad
+constexpr int PLANE_IT = (23 * 23 + 31) / 32;     // cp.async per lane and tile plane (bins of 16 x 16 cells in x, y)
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m)
+{
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((u64)hi << 32) | lo;
+}
 
 template <bool CPLX>
-__global__ void __launch_bounds__(32 * INTERP_NW, 1)
-rt_interp_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const int32_t *__restrict__ fine_offsets,
-                 const float *__restrict__ xs0, const float *__restrict__ xs1, const float *__restrict__ xs2,
-                 MutPtrPack vp, int C, const typename CellOf<float, CPLX>::type *__restrict__ us, int64_t ncells,
-                 float prefactor, const float *__restrict__ nu_weights)
+__global__ void __launch_bounds__(32 * INTERP_NW, 2)
+rt_interp_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__restrict__ xs0, const float *__restrict__ xs1,
+                 const float *__restrict__ xs2, MutPtrPack vp, int C, const typename CellOf<float, CPLX>::type *__restrict__ us,
+                 int64_t ncells, float prefactor, const float *__restrict__ nu_weights)
 {
     using Cell = typename CellOf<float, CPLX>::type;
     constexpr int NT = 32 * INTERP_NW;
+    constexpr int NG = CPLX ? 4 : 2;               // u64 registers per plane: complex (re, im) per slot; real (slot k, k + 1)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_bytes = (g.tile_cells * (int)sizeof(Cell) + 15) & ~15;
-    Cell *tiles[2] = {(Cell *)smem_raw, (Cell *)(smem_raw + tile_bytes)};
-    float *scr_s = (float *)(smem_raw + 2 * tile_bytes);              // [NW][2][SCR_F]
-    float *cs_s = scr_s + INTERP_NW * 2 * SCR_F;                      // [3][cs_stride]
+    Cell *tile = (Cell *)smem_raw;
+    float *rec_all = (float *)(smem_raw + tile_bytes);                // [NW][BATCH][REC_F]
+    float *cs_s = rec_all + INTERP_NW * BATCH * REC_F;                // [3][cs_stride]
     __shared__ int s_item[2][4];
+    __shared__ int s_batch;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Tx = g.T[0], Ty = g.T[1], Tz = g.T[2], Sx = g.S[0], S2 = g.S[2];
     const int total_items = a.item_start[a.nbins];
-    const LaneSlots ls = lane_slots(lane);
-    const int off0 = ls.g * Sx + ls.x, off3 = ls.y3 * Sx + ls.x3;
+    float *rec_w = rec_all + warp * BATCH * REC_F;
 
-    // role of this lane in the kernel evaluation: padded entry e of dimension rd
-    const int rd = lane < 12 ? 0 : (lane < 24 ? 1 : 2);
-    const int re = lane - 12 * rd;                                    // x, y: padded position 0..11; z: j = 0..7
-    const float *xs_r = rd == 0 ? xs0 : (rd == 1 ? xs1 : xs2);
-    const float *cs_r = cs_s + rd * kp.cs_stride;
-    const bool poly = kp.mode == NUFFT_EVAL_FAST && (kp.kind == NUFFT_KERNEL_KAISER_BESSEL || kp.kind == NUFFT_KERNEL_BACKWARDS_KAISER_BESSEL);
-    float *scr = scr_s + warp * 2 * SCR_F;
-    // scratch positions this lane writes (relative to the record)
-    int st_main;                                                      // main position
-    if (rd == 0) st_main = SCR_WX + re;
-    else if (rd == 1) st_main = SCR_WY + 4 * (re % 3) + re / 3;       // row y % 3, column y / 3 (y = 11 -> row2[3] = 0)
-    else st_main = SCR_WZ + re;
-    const bool y258 = rd == 1 && (re % 3) == 2 && re < 9;             // y in {2, 5, 8}: copies into rows 3..5
+    const LaneSlots ls = lane_slots(lane);
+    const int off0 = ls.g * Sx + ls.x, off3 = ls.y3 * Sx + ls.x3;     // slot k < 3: off0 + 3 k Sx
+    const int brev = (int)(__brev((unsigned)lane) >> 27);
 
     for (int i = tid; i < 3 * kp.cs_stride; i += NT) cs_s[i] = kp.cs[i];
-
-    // ---- tile staging (cp.async, one cell per lane; periodic wrap per row / column) ---------------------------
-    auto stage = [&](Cell *tile, int bin, int c) {
-        int b = bin;
-        const int bx = b % g.nb[0]; b /= g.nb[0];
-        const int by = b % g.nb[1]; b /= g.nb[1];
-        const int bz = b;
-        const Cell *u = us + (int64_t)c * ncells;
-        const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
-        const int x0 = bx * g.B[0] - (M - 1), y0 = by * g.B[1] - (M - 1), z0 = bz * g.B[2] - (M - 1);
-        for (int xb = 0; xb < Tx; xb += 32) {
-            const int x = xb + lane;
-            const bool in = x < Tx;
-            const int gx = wrap1(x0 + (in ? x : 0), Nx);
-            for (int z = 0; z < Tz; ++z) {
-                const int gz = wrap1(z0 + z, Nz);
-                const Cell *gplane = u + (int64_t)gz * Ny * Nx + gx;
-                Cell *tplane = tile + z * S2 + x;
-                for (int y = warp; y < Ty; y += INTERP_NW) {
-                    const int gy = wrap1(y0 + y, Ny);
-                    if (in) cp_async_cell<(int)sizeof(Cell)>(tplane + y * Sx, gplane + (int64_t)gy * Nx);
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
     if (tid == 0) {
         const int item = atomicAdd(a.work_counter, 1);
         s_item[0][0] = item;
         if (item < total_items) decode_item(a, item, g.chunk, s_item[0][1], s_item[0][2], s_item[0][3]);
+        s_batch = 0;
     }
     __syncthreads();
-    // flattened sequence of (item, component) steps; step s uses tile buffer s & 1
-    if (s_item[0][0] < total_items) stage(tiles[0], s_item[0][1], 0);
 
-    int step = 0;
     for (int it = 0;; ++it) {
         const int *cur = s_item[it & 1];
         if (cur[0] >= total_items) break;
@@ -115,139 +82,183 @@ rt_interp_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const int32_t *__
         const int by = b % g.nb[1]; b /= g.nb[1];
         const int bz = b;
         const int org0 = bx * g.B[0], org1 = by * g.B[1], org2 = bz * g.B[2];
-        const int org_r = rd == 0 ? org0 : (rd == 1 ? org1 : org2);
-        const int32_t *foff = fine_offsets + (int64_t)bin * g.nsub;
-        const int nzh = (g.sub[2] + 1) / 2;                           // register sub-bins per column
-        const int nrs = g.sub[0] * g.sub[1] * nzh;
+        const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
 
-        for (int c = 0; c < C; ++c, ++step) {
-            __syncthreads();          // s_item[next] visible; everybody is done with tile buffer (step + 1) & 1
-            // prefetch the tile of the next step, then wait for the current one
+        for (int c = 0; c < C; ++c) {
+            // ---- tile staging: lanes sweep the flattened (x, y) plane, warp w takes planes w, w + 4, ... ----------
             {
-                const int *nxt = s_item[(it + 1) & 1];
-                if (c + 1 < C) stage(tiles[(step + 1) & 1], bin, c + 1);
-                else if (nxt[0] < total_items) stage(tiles[(step + 1) & 1], nxt[1], 0);
-                else asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                const Cell *u = us + (int64_t)c * ncells;
+                const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
+                const int x0 = org0 - (M - 1), y0 = org1 - (M - 1), z0 = org2 - (M - 1);
+                const int nxy = Tx * Ty;
+                int goff[PLANE_IT], soff[PLANE_IT];
+#pragma unroll
+                for (int j = 0; j < PLANE_IT; ++j) {
+                    const int i = lane + 32 * j;
+                    const int y = i / Tx, x = i - y * Tx;
+                    const bool in = i < nxy;
+                    goff[j] = in ? wrap1(y0 + y, Ny) * Nx + wrap1(x0 + x, Nx) : -1;
+                    soff[j] = y * Sx + x;
+                }
+                for (int z = warp; z < Tz; z += INTERP_NW) {
+                    const Cell *gplane = u + (int64_t)wrap1(z0 + z, Nz) * Ny * Nx;
+                    Cell *tplane = tile + z * S2;
+#pragma unroll
+                    for (int j = 0; j < PLANE_IT; ++j)
+                        if (goff[j] >= 0) cp_async_cell<(int)sizeof(Cell)>(tplane + soff[j], gplane + goff[j]);
+                }
+                cp_async_wait_all();
             }
             __syncthreads();
-            const Cell *tile = tiles[step & 1];
 
-            for (int rs = warp; rs < nrs; rs += INTERP_NW) {
-                const int col = rs / nzh, zh = rs - col * nzh;
-                const int f0 = col * g.sub[2] + 2 * zh, f1 = min(f0 + 2, (col + 1) * g.sub[2]);
-                const int p0 = max(foff[f0], k0), p1 = min(foff[f1], k1);
-                if (p0 >= p1) continue;
-                const int cy = col / g.sub[0], cx = col - cy * g.sub[0];
-                // ---- register tile: planes 8 zh .. 8 zh + 14 (clamped to the tile), 4 slots per lane --------
-                float ur[ZP][4], ui[ZP][4];
+            // ---- batches of this item, pulled by the warps ------------------------------------------------------
+            int bi = 0;
+            if (lane == 0) bi = atomicAdd(&s_batch, 1);
+            bi = __shfl_sync(0xffffffffu, bi, 0);
+            float xq = 0.f, yq = 0.f, zq = 0.f;
+            {
+                const int k = k0 + bi * BATCH + lane;
+                if (bi < nbatches && k < k1) { xq = xs0[k]; yq = xs1[k]; zq = xs2[k]; }
+            }
+            while (bi < nbatches) {
+                const int kb = k0 + bi * BATCH;
+                const int nb = min(BATCH, k1 - kb);
+                // next batch of this warp: index and coordinates are fetched while this one is processed
+                int bn = 0;
+                if (lane == 0) bn = atomicAdd(&s_batch, 1);
+                bn = __shfl_sync(0xffffffffu, bn, 0);
+                const float x = xq, y = yq, z = zq;
                 {
-                    const Cell *base = tile + (4 * cy) * Sx + 4 * cx;
+                    const int k = k0 + bn * BATCH + lane;
+                    if (bn < nbatches && k < k1) { xq = xs0[k]; yq = xs1[k]; zq = xs2[k]; }
+                }
+                // output slot of this lane after the butterfly: point bitrev5(lane) of the batch
+                const bool has_out = brev < nb;
+                const int32_t n_out = has_out ? a.perm[kb + brev] : 0;
+
+                // ---- evaluate: one thread per point -----------------------------------------------------------
+                if (lane < nb) {
+                    float *r = rec_w + lane * REC_F;
+                    float w[W], pw[P];
+                    const int tx = eval_kernel_values<float, M>(kp, cs_s, 0, x, w) - org0;
+                    pad_shift(w, tx & 3, pw);
+                    float4 *q = reinterpret_cast<float4 *>(r + OFF_WX);
+                    q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                    q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+                    q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
+                    const int ty = eval_kernel_values<float, M>(kp, cs_s + kp.cs_stride, 1, y, w) - org1;
+                    pad_shift(w, ty & 3, pw);
+                    store_y(r, pw);
+                    const int tz = eval_kernel_values<float, M>(kp, cs_s + 2 * kp.cs_stride, 2, z, w) - org2;
 #pragma unroll
-                    for (int q = 0; q < ZP; ++q) {
-                        const int z = min(ZB * zh + q, Tz - 1);
-                        const Cell *pl = base + z * S2;
-                        const Cell t0 = pl[off0], t1 = pl[off0 + 3 * Sx], t2 = pl[off0 + 6 * Sx], t3 = pl[off3];
+                    for (int j = 0; j < W; ++j) r[IOFF_WZ + ((tz + j) & 7)] = w[j];
+                    reinterpret_cast<int *>(r)[IOFF_KEY] = ((ty >> 2) << 12) | ((tx >> 2) << 8) | tz;
+                }
+                __syncwarp();
+
+                // ---- accumulate ---------------------------------------------------------------------------------
+                u64 G[8][NG];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int k = 0; k < NG; ++k) G[i][k] = 0ull;
+                int cur_col = -1, hi = 0;                 // planes [.., hi) of column cur_col are in registers
+                u64 c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, res = 0;
+                const float *pY = rec_w + OFF_WY + 4 * ls.row, *pX = rec_w + OFF_WX + ls.x, *pX3 = rec_w + OFF_WX + ls.x3;
+
+                auto load_plane = [&](const Cell *cb, int zp) {
+                    const Cell *pl = cb + zp * S2;
+                    switch (zp & 7) {
+#define NUFFT_RT_SET(I)                                                                                       \
+    case I:                                                                                                   \
+        if constexpr (CPLX) {                                                                                 \
+            lds64_inplace(G[I][0], pl + off0); lds64_inplace(G[I][1], pl + off0 + 3 * Sx);                    \
+            lds64_inplace(G[I][2], pl + off0 + 6 * Sx); lds64_inplace(G[I][3], pl + off3);                    \
+        } else {                                                                                              \
+            lds32x2_inplace(G[I][0], pl + off0, pl + off0 + 3 * Sx);                                          \
+            lds32x2_inplace(G[I][1], pl + off0 + 6 * Sx, pl + off3);                                          \
+        }                                                                                                     \
+        break;
+                        NUFFT_RT_SET(0) NUFFT_RT_SET(1) NUFFT_RT_SET(2) NUFFT_RT_SET(3)
+                        NUFFT_RT_SET(4) NUFFT_RT_SET(5) NUFFT_RT_SET(6) NUFFT_RT_SET(7)
+#undef NUFFT_RT_SET
+                    }
+                };
+                auto xchg = [&](u64 ea, u64 la, int m) -> u64 {     // earlier point stays in lanes with bit m clear
+                    const bool bit = (lane & m) != 0;
+                    const u64 send = bit ? ea : la, keep = bit ? la : ea;
+                    return fadd2(keep, shfl_xor_u64(send, m));
+                };
+
+                for (int p = 0; p < BATCH; ++p) {
+                    u64 v = 0ull;
+                    if (p < nb) {
+                        const float *r = rec_w + p * REC_F;
+                        const int key = reinterpret_cast<const int *>(r)[IOFF_KEY];
+                        const float4 za = *reinterpret_cast<const float4 *>(r + IOFF_WZ);
+                        const float4 zb = *reinterpret_cast<const float4 *>(r + IOFF_WZ + 4);
+                        const float4 wy = *reinterpret_cast<const float4 *>(pY + p * REC_F);
+                        const float wx = pX[p * REC_F], wx3 = pX3[p * REC_F];
+                        const int col = key >> 8, tz = key & 0xff;
+                        if (col != cur_col) { cur_col = col; hi = 0; }
+                        if (hi < tz + 8) {
+                            const Cell *cb = tile + (4 * (col >> 4)) * Sx + 4 * (col & 15);
+                            for (int zp = max(hi, tz); zp < tz + 8; ++zp) load_plane(cb, zp);
+                            hi = tz + 8;
+                        }
+                        const float wz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                        u64 h[NG];
+#pragma unroll
+                        for (int k = 0; k < NG; ++k) h[k] = fmul2(pk2(wz[0], wz[0]), G[0][k]);
+#pragma unroll
+                        for (int i = 1; i < 8; ++i)
+#pragma unroll
+                            for (int k = 0; k < NG; ++k) h[k] = ffma2(pk2(wz[i], wz[i]), G[i][k], h[k]);
+                        const u64 w01 = fmul2(pk2(wx, wx), pk2(wy.x, wy.y));
+                        const u64 w23 = fmul2(pk2(wx, wx3), pk2(wy.z, wy.w));
                         if constexpr (CPLX) {
-                            ur[q][0] = t0.x; ui[q][0] = t0.y; ur[q][1] = t1.x; ui[q][1] = t1.y;
-                            ur[q][2] = t2.x; ui[q][2] = t2.y; ur[q][3] = t3.x; ui[q][3] = t3.y;
+                            const float2 wa = unpk2(w01), wb = unpk2(w23);
+                            v = fmul2(pk2(wa.x, wa.x), h[0]);
+                            v = ffma2(pk2(wa.y, wa.y), h[1], v);
+                            v = ffma2(pk2(wb.x, wb.x), h[2], v);
+                            v = ffma2(pk2(wb.y, wb.y), h[3], v);
                         } else {
-                            ur[q][0] = t0; ur[q][1] = t1; ur[q][2] = t2; ur[q][3] = t3;
-                            ui[q][0] = ui[q][1] = ui[q][2] = ui[q][3] = 0.f;
+                            v = ffma2(w23, h[1], fmul2(w01, h[0]));      // (slots 0 + 2, slots 1 + 3): summed at the end
                         }
                     }
+                    // streaming butterfly: a binary counter of partial transposes (levels xor 16, 8, 4, 2, 1)
+                    if (!(p & 1)) { c0 = v; continue; }
+                    v = xchg(c0, v, 16);
+                    if (!(p & 2)) { c1 = v; continue; }
+                    v = xchg(c1, v, 8);
+                    if (!(p & 4)) { c2 = v; continue; }
+                    v = xchg(c2, v, 4);
+                    if (!(p & 8)) { c3 = v; continue; }
+                    v = xchg(c3, v, 2);
+                    if (!(p & 16)) { c4 = v; continue; }
+                    res = xchg(c4, v, 1);
                 }
-                float xr = xs_r[p0];
-                int n_next = a.perm[p0];
-                for (int p = p0; p < p1; ++p) {
-                    const float x = xr;
-                    const int n = n_next;
-                    if (p + 1 < p1) { xr = xs_r[p + 1]; n_next = a.perm[p + 1]; }
-                    // ---- kernel value of this lane's padded entry -------------------------------------------
-                    float r;
-                    const int i0 = point_to_cell0<float>(x, kp.N[rd], r);
-                    const int t = i0 - org_r;                         // local cell of the point in the bin
-                    const int j = rd == 2 ? re : re - (t & 3);        // kernel value index of this entry
-                    const bool on = j >= 0 && j < W;
-                    float wv;
-                    if (poly) {
-                        // piecewise polynomial (KB / BKB fast mode): Horner on this lane's coefficient column,
-                        // same operation order as eval_kernel_values
-                        const int jc = on ? j : 0;
-                        const float xt = 2.f * (r - (float)i0) - 1.f;
-                        wv = cs_r[(M + 3) * W + jc];
-#pragma unroll
-                        for (int q = M + 2; q >= 0; --q) wv = fmaf(xt, wv, cs_r[q * W + jc]);
-                    } else {
-                        float wall[W];
-                        eval_kernel_values<float, M>(kp, cs_r, rd, x, wall);   // other kernels / Direct mode
-                        wv = 0.f;
-#pragma unroll
-                        for (int jj = 0; jj < W; ++jj) wv = (jj == j) ? wall[jj] : wv;
-                    }
-                    if (!on) wv = 0.f;
-                    float *sc = scr + (p & 1) * SCR_F;
-                    sc[st_main] = wv;
-                    if (y258) {
-                        const int cc = re / 3;
-                        sc[SCR_WY + 12 + cc] = wv; sc[SCR_WY + 16 + cc] = wv; sc[SCR_WY + 20 + cc] = wv;
-                        sc[SCR_WY + 12 + 4 * cc + 3] = wv;
-                    }
-                    const int tzl = __shfl_sync(0xffffffffu, t, 24) - ZB * zh;     // local z start in the register tile
-                    __syncwarp();
-                    const float4 wza = *reinterpret_cast<const float4 *>(sc + SCR_WZ);
-                    const float4 wzb = *reinterpret_cast<const float4 *>(sc + SCR_WZ + 4);
-                    const float4 wy = *reinterpret_cast<const float4 *>(sc + SCR_WY + 4 * ls.row);
-                    const float wx = sc[SCR_WX + ls.x], wx3 = sc[SCR_WX + ls.x3];
-                    const float w0 = wx * wy.x, w1 = wx * wy.y, w2 = wx * wy.z, w3 = wx3 * wy.w;
-                    float accr = 0.f, acci = 0.f;
-#define NUFFT_RT_PL(Q, WZ)                                                                                  \
-    {                                                                                                       \
-        float tr = ur[Q][0] * w0;                                                                           \
-        tr = fmaf(ur[Q][1], w1, tr); tr = fmaf(ur[Q][2], w2, tr); tr = fmaf(ur[Q][3], w3, tr);              \
-        accr = fmaf(tr, WZ, accr);                                                                          \
-        if constexpr (CPLX) {                                                                               \
-            float ti = ui[Q][0] * w0;                                                                       \
-            ti = fmaf(ui[Q][1], w1, ti); ti = fmaf(ui[Q][2], w2, ti); ti = fmaf(ui[Q][3], w3, ti);          \
-            acci = fmaf(ti, WZ, acci);                                                                      \
-        }                                                                                                   \
-    }
-#define NUFFT_RT_CASE(T0)                                                                                   \
-    case T0:                                                                                                \
-        NUFFT_RT_PL(T0 + 0, wza.x) NUFFT_RT_PL(T0 + 1, wza.y) NUFFT_RT_PL(T0 + 2, wza.z) NUFFT_RT_PL(T0 + 3, wza.w) \
-        NUFFT_RT_PL(T0 + 4, wzb.x) NUFFT_RT_PL(T0 + 5, wzb.y) NUFFT_RT_PL(T0 + 6, wzb.z) NUFFT_RT_PL(T0 + 7, wzb.w) \
-        break;
-                    switch (tzl) {
-                        NUFFT_RT_CASE(0) NUFFT_RT_CASE(1) NUFFT_RT_CASE(2) NUFFT_RT_CASE(3)
-                        NUFFT_RT_CASE(4) NUFFT_RT_CASE(5) NUFFT_RT_CASE(6)
-                    default:
-                        NUFFT_RT_PL(7, wza.x) NUFFT_RT_PL(8, wza.y) NUFFT_RT_PL(9, wza.z) NUFFT_RT_PL(10, wza.w)
-                        NUFFT_RT_PL(11, wzb.x) NUFFT_RT_PL(12, wzb.y) NUFFT_RT_PL(13, wzb.z) NUFFT_RT_PL(14, wzb.w)
-                        break;
-                    }
-#undef NUFFT_RT_CASE
-#undef NUFFT_RT_PL
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        accr += __shfl_xor_sync(0xffffffffu, accr, o);
-                        if constexpr (CPLX) acci += __shfl_xor_sync(0xffffffffu, acci, o);
-                    }
-                    if (lane == 0) {
-                        const float scale = prefactor * (nu_weights ? nu_weights[n] : 1.f);
-                        if constexpr (CPLX) store_value<float, true>(vp.p[c], n, make_float2(accr * scale, acci * scale));
-                        else store_value<float, false>(vp.p[c], n, accr * scale);
-                    }
+                // ---- store -----------------------------------------------------------------------------------------
+                if (has_out) {
+                    const float2 rv = unpk2(res);
+                    float sc = prefactor;
+                    if (nu_weights) sc *= nu_weights[n_out];
+                    if constexpr (CPLX) store_value<float, true>(vp.p[c], n_out, make_float2(rv.x * sc, rv.y * sc));
+                    else store_value<float, false>(vp.p[c], n_out, (rv.x + rv.y) * sc);
                 }
+                __syncwarp();
+                bi = bn;
             }
+            __syncthreads();                 // every warp is done with the tile (and with s_batch)
+            if (tid == 0) s_batch = 0;
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 inline size_t interp_smem_bytes(const TileGeom &g, int cs_stride, size_t cell_bytes)
 {
-    size_t b = 2 * (((size_t)g.tile_cells * cell_bytes + 15) & ~(size_t)15);
-    b += (size_t)INTERP_NW * 2 * SCR_F * sizeof(float);
+    size_t b = ((size_t)g.tile_cells * cell_bytes + 15) & ~(size_t)15;
+    b += (size_t)INTERP_NW * BATCH * REC_F * sizeof(float);
     b += (size_t)(3 * cs_stride + 4) * sizeof(float);
     return b + 16;
 }

@@ -33,7 +33,7 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
             if (p.geom.rt && p.method == NUFFT_METHOD_SHARED_MEMORY) {
                 auto kern = rt::rt_spread_kernel<CPLX>;
                 const size_t smem = rt::spread_smem_bytes(p.geom, p.cs_stride, sizeof(Cell));
-                const int nthreads = 32 * (rt::SPREAD_NCONS + rt::SPREAD_NPROD);
+                const int nthreads = 32 * rt::SPREAD_NWARP;
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int occ = 0, nsm = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem));

@@ -427,15 +427,16 @@ class PlanNUFFT:
         return p, o, tuple(int(bd[d]) for d in range(self._ndims))
 
     def binning_fine(self):
-        """(perm, fine_offsets, sub_dims): the (bin, sub-bin) order the kernels use (register-tile fast path);
-        identical to `binning()` with sub_dims == (1, 1, 1) on other plans."""
+        """(perm, fine_offsets, sub_dims): the (bin, sub-bin) order the kernels use.  Plans on the register-window
+        fast path refine every bin into sub_dims sub-bins (4 x 4-cell columns, single cells along z) and do not
+        materialise sub-bin offsets (fine_offsets is None); other plans: identical to `binning()`, sub_dims (1, 1, 1)."""
         perm, off = C.c_void_p(), C.c_void_p()
         nf = C.c_int64()
         sd = (C.c_int64 * 3)()
         _check(self._lib.nufft_get_binning_fine(self._h, C.byref(perm), C.byref(off), C.byref(nf), sd))
         p = _tensor_from_ptr(perm.value, (self.Np,), torch.int32, self.device, self) if self.Np else \
             torch.empty(0, dtype=torch.int32, device=self.device)
-        o = _tensor_from_ptr(off.value, (nf.value + 1,), torch.int32, self.device, self)
+        o = _tensor_from_ptr(off.value, (nf.value + 1,), torch.int32, self.device, self) if off.value else None
         return p, o, tuple(int(sd[d]) for d in range(3))
 
     def kernel_info(self, d: int = 0):
