@@ -28,7 +28,7 @@ CFLAGS = ([f"-DNUFFT_DEV_M={DEV_M}"] if DEV_M else []) + ["-O3", "-lineinfo", "-
           "-ccbin", shutil.which("g++") or "g++", "-Xptxas", "-v", "-Xfatbin", "-compress-all"]
 
 # (source, object suffix, extra defines)
-UNITS = [("api.cu", "", []), ("host_plan.cu", "", []), ("binning.cu", "", []), ("deconv.cu", "", [])]
+UNITS = [("api.cu", "", []), ("host_plan.cu", "", []), ("binning.cu", "", []), ("deconv.cu", "", []), ("pfft.cu", "", [])]
 for t in ("float", "double"):
     for c in (0, 1):
         tag = f"_{'f32' if t == 'float' else 'f64'}_{'c' if c else 'r'}"

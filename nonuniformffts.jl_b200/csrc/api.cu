@@ -214,9 +214,14 @@ int nufft_type1_finish(nufft_plan h, void *const uhat[], const nufft_callbacks *
     if (!uhat) { set_error("null uhat"); return NUFFT_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(p.device));
     rec(p, 5);
-    NUFFT_TRY(fft_forward(p));
-    rec(p, 6);
-    NUFFT_TRY(deconv_type1_run(p, uhat, cb));
+    if (p.pfft) {
+        NUFFT_TRY(pfft_type1_run(p, uhat, cb));     // truncating FFT passes with the deconvolution fused in
+        rec(p, 6);
+    } else {
+        NUFFT_TRY(fft_forward(p));
+        rec(p, 6);
+        NUFFT_TRY(deconv_type1_run(p, uhat, cb));
+    }
     rec(p, 7);
     p.ev_rec[2] = true;
     return NUFFT_SUCCESS;
@@ -238,9 +243,14 @@ int nufft_type2_prepare(nufft_plan h, const void *const uhat[], const nufft_call
     if (!uhat) { set_error("null uhat"); return NUFFT_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(p.device));
     rec(p, 8);
-    NUFFT_TRY(deconv_type2_run(p, uhat, cb));
-    rec(p, 9);
-    NUFFT_TRY(fft_backward(p));
+    if (p.pfft) {
+        rec(p, 9);
+        NUFFT_TRY(pfft_type2_run(p, uhat, cb));     // zero-padding FFT passes with the deconvolution fused in
+    } else {
+        NUFFT_TRY(deconv_type2_run(p, uhat, cb));
+        rec(p, 9);
+        NUFFT_TRY(fft_backward(p));
+    }
     rec(p, 10);
     p.ev_rec[3] = true;
     return NUFFT_SUCCESS;
@@ -316,7 +326,8 @@ int nufft_describe(nufft_plan h, char *buf, size_t buflen)
              "  - frequency order: %s (fftshift = %s)\n"
              "  - block size: (%d, %d, %d) (excluding 2M - 1 = %d ghost cells in each direction), %lld bins\n"
              "  - GPU method: :%s\n"
-             "  - tile (shared memory): (%d, %d, %d) cells, row stride %d, batch %d points, chunk %d points\n",
+             "  - FFT: %s\n"
+             "  - tile (shared memory): (%d, %d, %d) cells, row stride %d, batch %d points, chunk %d points%s\n",
              p.D, p.cplx ? "Complex" : "", p.f64 ? "Float64" : "Float32", knames[p.opts.kernel], shape, p.h_shape[0], p.M,
              p.opts.eval_mode == NUFFT_EVAL_FAST ? "FastApproximation" : "Direct", sigma,
              (long long)p.nk[0], (long long)p.nk[1], (long long)p.nk[2],
@@ -324,7 +335,8 @@ int nufft_describe(nufft_plan h, char *buf, size_t buflen)
              p.opts.fftshift ? "increasing" : "FFTW", p.opts.fftshift ? "true" : "false",
              g.B[0], g.B[1], g.B[2], 2 * p.M - 1, (long long)p.nbins,
              p.method == NUFFT_METHOD_SHARED_MEMORY ? "shared_memory" : "global_memory",
-             g.T[0], g.T[1], g.T[2], g.S[0], g.batch, g.chunk);
+             p.pfft ? "pruned 1-D passes fused with deconvolution (pfft.cu)" : "cuFFT + separate deconvolution",
+             g.T[0], g.T[1], g.T[2], g.S[0], g.batch, g.chunk, g.rt ? ", register-window kernels" : "");
     return NUFFT_SUCCESS;
 }
 

@@ -164,6 +164,11 @@ struct Plan {
     bool fft_ok = false;
     void *d_fft_work = nullptr;
     size_t fft_work_bytes = 0;
+    // pruned FFT fused with deconvolution (pfft.cu): twiddle tables per dimension and the first intermediate array
+    bool pfft = false;
+    void *d_pf_tw[3] = {nullptr, nullptr, nullptr};
+    void *d_pf_iph[3] = {nullptr, nullptr, nullptr};   // 1 / phihat per dimension
+    void *d_pf_a = nullptr;
 
     // binning state
     TileGeom geom{};
@@ -221,6 +226,11 @@ int spread_run(Plan &p, const void *const vp[], const nufft_callbacks *cb); // s
 int interp_run(Plan &p, void *const vp[], const nufft_callbacks *cb);       // interp_*.cu
 int deconv_type1_run(Plan &p, void *const uhat[], const nufft_callbacks *cb); // deconv.cu
 int deconv_type2_run(Plan &p, const void *const uhat[], const nufft_callbacks *cb);
+bool pfft_eligible(const Plan &p);            // pfft.cu
+int pfft_init(Plan &p);
+void pfft_free(Plan &p);
+int pfft_type1_run(Plan &p, void *const uhat[], const nufft_callbacks *cb);        // FFT + truncation + deconvolution
+int pfft_type2_run(Plan &p, const void *const uhat[], const nufft_callbacks *cb);  // deconvolution + padding + FFT
 int fft_forward(Plan &p);
 int fft_backward(Plan &p);
 int scan_u32(Plan &p, uint32_t *data, int64_t n, bool inclusive);          // binning.cu (in place prefix sum)

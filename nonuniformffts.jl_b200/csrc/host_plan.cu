@@ -467,10 +467,15 @@ int host_plan_init(Plan &p)
         return NUFFT_ERR_ALLOC;
     }
 
+    // pruned FFT fused with deconvolution (pfft.cu) when the plan is eligible; cuFFT + K-deconv otherwise
+    p.pfft = pfft_eligible(p);
+    if (p.pfft) NUFFT_TRY(pfft_init(p));
+
     // cuFFT plans: Julia dims are column-major -> reversed for cuFFT; batch = ntransforms
     int n[3];
     for (int d = 0; d < p.D; ++d) n[d] = (int)p.Nos[p.D - 1 - d];
     size_t ws_fw = 0, ws_bw = 0;
+    if (!p.pfft) {
     CUFFT_TRY(cufftCreate(&p.fft_fw));
     CUFFT_TRY(cufftCreate(&p.fft_bw));
     p.fft_ok = true;
@@ -496,6 +501,7 @@ int host_plan_init(Plan &p)
     }
     CUFFT_TRY(cufftSetStream(p.fft_fw, p.stream));
     CUFFT_TRY(cufftSetStream(p.fft_bw, p.stream));
+    }
 
     // binning tables that depend only on the plan
     CUDA_TRY(cudaMalloc(&p.d_bin_offsets, (size_t)(p.nbins + 1) * sizeof(int32_t)));
@@ -512,6 +518,7 @@ int host_plan_init(Plan &p)
 void host_plan_free(Plan &p)
 {
     if (p.fft_ok) { cufftDestroy(p.fft_fw); cufftDestroy(p.fft_bw); p.fft_ok = false; }
+    pfft_free(p);
     auto f = [](auto *&ptr) { if (ptr) { cudaFree((void *)ptr); ptr = nullptr; } };
     f(p.d_fft_work);
     if (!p.cplx) f(p.d_uhat);

@@ -190,3 +190,36 @@ def test_empty_and_tiny(nufft, oracle_mod):
     out = torch.full(gp.shape, 7.0, dtype=torch.complex128, device="cuda")
     gp.exec_type1(out, torch.empty(0, dtype=torch.float64, device="cuda"))
     assert float(out.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_pruned_fft_paths(nufft, oracle_mod, dtype):
+    # power-of-two oversampled sizes -> truncating / zero-padding FFT passes fused with the deconvolution (pfft.cu);
+    # odd kept sizes exercise the index maps (31 -> 64, 63 -> 128 oversampled cells)
+    run_case(nufft, oracle_mod, dtype, (31, 32, 63), 8000, sigma=2.0, seed=40)
+    run_case(nufft, oracle_mod, dtype, (31, 32, 63), 8000, sigma=2.0, fftshift=True, C=2, callbacks=True, seed=41)
+    run_case(nufft, oracle_mod, dtype, (63, 32), 4000, sigma=2.0, fftshift=True, callbacks=True, seed=42)
+    run_case(nufft, oracle_mod, dtype, (255,), 500, sigma=2.0, callbacks=True, seed=43)
+    run_case(nufft, oracle_mod, dtype, (8, 16, 8), 500, sigma=2.0, seed=44)        # smallest supported lines (16)
+
+
+def test_pruned_fft_vs_cufft(nufft, monkeypatch):
+    """The fused pruned passes and cuFFT + K-deconv are two implementations of the same linear map."""
+    import torch
+    rng = np.random.default_rng(45)
+    dims, Np = (64, 32, 128), 30000
+    xs = tuple(torch.from_numpy((rng.random(Np) * 2 * np.pi).astype(np.float32)).cuda() for _ in dims)
+    vp = torch.from_numpy((rng.standard_normal(Np) + 1j * rng.standard_normal(Np)).astype(np.complex64)).cuda()
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("NUFFT_B200_PFFT", flag)
+        gp = gpu_plan(nufft, np.complex64, dims, m=4, sigma=2.0)
+        assert ("pruned" in repr(gp)) == (flag == "1")
+        gp.set_points(xs)
+        u = torch.empty(gp.shape, dtype=torch.complex64, device="cuda")
+        gp.exec_type1(u, vp)
+        v = torch.empty(Np, dtype=torch.complex64, device="cuda")
+        gp.exec_type2(v, u)
+        outs.append((u.cpu().numpy(), v.cpu().numpy()))
+        gp.close()
+    assert l2_error(outs[0][0], outs[1][0]) <= 2e-6 and l2_error(outs[0][1], outs[1][1]) <= 2e-6
