@@ -28,6 +28,7 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+static_assert(SORT_THREADS == RADIX, "radix_scatter_kernel: one thread per digit");
 
 struct BinGeom {
     int D;
@@ -40,11 +41,22 @@ struct BinGeom {
     int nsub;
 };
 
+// interleaved record of the folded coordinates of one point (D > 1): float4 / double4
+template <typename T> struct PointRec;
+template <> struct PointRec<float> {
+    using type = float4;
+    __device__ static __forceinline__ float4 make(float a, float b, float c) { return make_float4(a, b, c, 0.f); }
+};
+template <> struct PointRec<double> {
+    using type = double4;
+    __device__ static __forceinline__ double4 make(double a, double b, double c) { return make_double4(a, b, c, 0.); }
+};
+
 // ---- keys --------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
 bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
-                uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count)
+                uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count, typename PointRec<T>::type *__restrict__ rec)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -54,18 +66,21 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
         uint32_t key = 0xffffffffu;
         if (valid) {
             T r;
-            int c = point_to_cell0<T>(fold_point<T>(x0[i], g.convention), g.N[0], r);
+            T f0 = fold_point<T>(x0[i], g.convention), f1 = (T)0, f2 = (T)0;
+            int c = point_to_cell0<T>(f0, g.N[0], r);
             int b = c / g.B[0];
             uint32_t k = (uint32_t)b;
             int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // rt: 4-cell columns in x, y; single cells in z
             if (g.D > 1) {
-                c = point_to_cell0<T>(fold_point<T>(x1[i], g.convention), g.N[1], r);
+                f1 = fold_point<T>(x1[i], g.convention);
+                c = point_to_cell0<T>(f1, g.N[1], r);
                 b = c / g.B[1];
                 sy = (c - b * g.B[1]) >> 2;
                 k += (uint32_t)b * (uint32_t)g.nb[0];
             }
             if (g.D > 2) {
-                c = point_to_cell0<T>(fold_point<T>(x2[i], g.convention), g.N[2], r);
+                f2 = fold_point<T>(x2[i], g.convention);
+                c = point_to_cell0<T>(f2, g.N[2], r);
                 b = c / g.B[2];
                 sz = c - b * g.B[2];
                 k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
@@ -74,6 +89,8 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
             // ordered along z; the histogram stays per bin
             key = k;
             keys[i] = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
+            // folded coordinates as one 16- / 32-byte record: the gather after the sort then touches one sector per point
+            if (rec) rec[i] = PointRec<T>::make(f0, f1, f2);
         }
         // warp-aggregated histogram: one atomic per distinct bin in the warp (clustered inputs)
         const unsigned active = __ballot_sync(0xffffffffu, valid);
@@ -204,7 +221,8 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint3
     for (int i = threadIdx.x; i < RADIX; i += SORT_THREADS) hist[(size_t)i * nblk + blockIdx.x] = h[i];
 }
 
-// Stable scatter.  Order inside a CTA tile: warp-major, then iteration k, then lane (== index order).
+// Stable scatter.  Order inside a CTA tile: warp-major, then iteration k, then lane (== index order).  The tile is first
+// reordered by digit in shared memory so that the global writes are runs of consecutive addresses per digit.
 template <bool FIRST, bool LAST>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
@@ -212,19 +230,31 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__rest
                      uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out)
 {
     __shared__ uint32_t warp_cnt[SORT_WARPS][RADIX];
-    __shared__ uint32_t digit_base[RADIX];
+    __shared__ uint32_t digit_base[RADIX];       // global position of the first element of (digit, this CTA)
+    __shared__ uint32_t local_off[RADIX];        // position of the digit's first element inside the reordered tile
+    __shared__ uint32_t scan_tmp[40];
+    __shared__ uint32_t s_keys[SORT_TILE];
+    __shared__ int32_t s_vals[SORT_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&warp_cnt[0][0])[i] = 0;
     __syncthreads();
 
-    const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)warp * (32 * SORT_ITEMS);
+    const int64_t tbase = (int64_t)blockIdx.x * SORT_TILE;
+    const int64_t wbase = tbase + (int64_t)warp * (32 * SORT_ITEMS);
+    const int ntile = (int)(n - tbase < SORT_TILE ? n - tbase : SORT_TILE);
     uint32_t key[SORT_ITEMS];
     uint32_t rank[SORT_ITEMS];
+    int32_t val[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        key[k] = i < n ? keys_in[i] : 0u;
+        val[k] = FIRST ? (int32_t)i : (i < n ? vals_in[i] : 0);
+    }
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
         const int64_t i = wbase + k * 32 + lane;
         const bool valid = i < n;
-        key[k] = valid ? keys_in[i] : 0u;
         const uint32_t digit = (key[k] >> shift) & (RADIX - 1);
         const uint32_t tag = valid ? digit : (uint32_t)(RADIX + lane);   // invalid lanes never match anyone
         const unsigned peers = __match_any_sync(0xffffffffu, tag);
@@ -239,8 +269,10 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__rest
         __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive scan over the warps of this CTA + global base of (digit, CTA)
-    for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) {
+    // per digit (one thread each): exclusive scan over the warps of this CTA, CTA total, global base of (digit, CTA)
+    uint32_t total = 0;
+    {
+        const int d = threadIdx.x;               // SORT_THREADS == RADIX
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w) {
@@ -248,7 +280,13 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__rest
             warp_cnt[w][d] = run;
             run += t;
         }
+        total = run;
         digit_base[d] = hist_scanned[(size_t)d * nblk + blockIdx.x];
+    }
+    {
+        uint32_t sum;
+        const uint32_t ex = block_exclusive_scan(total, scan_tmp, sum);
+        local_off[threadIdx.x] = ex;
     }
     __syncthreads();
 #pragma unroll
@@ -256,10 +294,18 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__rest
         const int64_t i = wbase + k * 32 + lane;
         if (i < n) {
             const uint32_t digit = (key[k] >> shift) & (RADIX - 1);
-            const uint32_t pos = digit_base[digit] + warp_cnt[warp][digit] + rank[k];
-            if (!LAST) keys_out[pos] = key[k];
-            vals_out[pos] = FIRST ? (int32_t)i : vals_in[i];
+            const uint32_t lpos = local_off[digit] + warp_cnt[warp][digit] + rank[k];
+            s_keys[lpos] = key[k];
+            s_vals[lpos] = val[k];
         }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntile; t += SORT_THREADS) {
+        const uint32_t kk = s_keys[t];
+        const uint32_t digit = (kk >> shift) & (RADIX - 1);
+        const uint32_t pos = digit_base[digit] + ((uint32_t)t - local_off[digit]);
+        if (!LAST) keys_out[pos] = kk;
+        vals_out[pos] = s_vals[t];
     }
 }
 
@@ -267,15 +313,17 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__rest
 template <typename T>
 __global__ void __launch_bounds__(256)
 gather_points_kernel(int D, int convention, int64_t np, const int32_t *__restrict__ perm,
-                     const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
+                     const T *__restrict__ x0, const typename PointRec<T>::type *__restrict__ rec,
                      T *__restrict__ y0, T *__restrict__ y1, T *__restrict__ y2)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= np) return;
     const int32_t i = perm[k];
-    y0[k] = fold_point<T>(x0[i], convention);
-    if (D > 1) y1[k] = fold_point<T>(x1[i], convention);
-    if (D > 2) y2[k] = fold_point<T>(x2[i], convention);
+    if (D == 1) { y0[k] = fold_point<T>(x0[i], convention); return; }
+    const typename PointRec<T>::type r = rec[i];          // folded in bin_keys_kernel: one sector per point
+    y0[k] = r.x;
+    y1[k] = r.y;
+    if (D > 2) y2[k] = r.z;
 }
 
 // bin_count[b+1] holds the count of bin b -> items[b+1] = ceil(count / chunk); [0] = 0
@@ -325,6 +373,7 @@ static int ensure_capacity(Plan &p, int64_t np)
     auto f = [](auto *&ptr) { if (ptr) { cudaFree((void *)ptr); ptr = nullptr; } };
     f(p.d_keys[0]); f(p.d_keys[1]); f(p.d_vals[0]); f(p.d_vals[1]);
     for (int d = 0; d < 3; ++d) f(p.d_xs[d]);
+    f(p.d_rec);
     const int64_t cap = np + np / 8 + 1024;   // head-room: no reallocation when Np fluctuates
     p.cap = 0;
     cudaError_t e = cudaSuccess;
@@ -333,6 +382,7 @@ static int ensure_capacity(Plan &p, int64_t np)
         if (e == cudaSuccess) e = cudaMalloc(&p.d_vals[i], (size_t)cap * sizeof(int32_t));
     }
     for (int d = 0; d < p.D && e == cudaSuccess; ++d) e = cudaMalloc(&p.d_xs[d], (size_t)cap * p.real_bytes);
+    if (p.D > 1 && e == cudaSuccess) e = cudaMalloc(&p.d_rec, (size_t)cap * 4 * p.real_bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
         set_error("cannot allocate point buffers for %lld points", (long long)np);
@@ -360,7 +410,8 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
     if (np > 0) {
         const int grid = (int)std::min<int64_t>(cdiv(np, 256), 148 * 16);
-        bin_keys_kernel<T><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count);
+        bin_keys_kernel<T><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count,
+                                                 p.D > 1 ? (typename PointRec<T>::type *)p.d_rec : nullptr);
         NUFFT_COUNT_LAUNCH();
     }
     // slot b+1 holds the count of bin b and slot 0 stays 0: an inclusive scan of this array is exactly
@@ -428,8 +479,8 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
     }
     if (np > 0) {
         gather_points_kernel<T><<<(unsigned)cdiv(np, 256), 256, 0, st>>>(
-            p.D, p.opts.point_convention, np, p.d_perm, (const T *)x[0], p.D > 1 ? (const T *)x[1] : nullptr,
-            p.D > 2 ? (const T *)x[2] : nullptr, (T *)p.d_xs[0], (T *)p.d_xs[1], (T *)p.d_xs[2]);
+            p.D, p.opts.point_convention, np, p.d_perm, (const T *)x[0], (const typename PointRec<T>::type *)p.d_rec,
+            (T *)p.d_xs[0], (T *)p.d_xs[1], (T *)p.d_xs[2]);
         NUFFT_COUNT_LAUNCH();
     }
     // work items: bins with more than `chunk` points are split

@@ -181,6 +181,7 @@ struct Plan {
     int32_t *d_vals[2] = {nullptr, nullptr};
     int32_t *d_perm = nullptr;       // alias into d_vals
     void *d_xs[3] = {nullptr, nullptr, nullptr};       // sorted, folded coordinates (T)
+    void *d_rec = nullptr;                             // folded coordinates in input order, one 4 x T record per point (D > 1)
     int32_t *d_bin_offsets = nullptr;                  // nbins + 1
     int32_t *d_perm_coarse = nullptr;                  // rt plans: bin-stable permutation, built on demand (introspection)
     int64_t perm_coarse_cap = 0;
@@ -214,6 +215,7 @@ static inline int record_size(int D, int M)
 
 // floats per point record of the register-tile kernels (rt_common.cuh)
 constexpr int RT_REC_F = 52;
+constexpr int RT_SREC_F = 60;      // spreading records carry value x wz (complex): rt_spread.cuh
 
 // kernel-launch helper: ceil-div
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -293,7 +293,7 @@ static bool choose_geometry(Plan &p)
         }
         auto rt_need = [&](int bz) -> size_t {
             const size_t tile = (size_t)(16 + W - 1) * (16 + W - 1) * (bz + W - 1) * cell_bytes;
-            return tile + (size_t)4 * 32 * RT_REC_F * sizeof(float) + ((size_t)D * p.cs_stride + 4) * p.real_bytes + 256;
+            return tile + (size_t)4 * 32 * RT_SREC_F * sizeof(float) + ((size_t)D * p.cs_stride + 4) * p.real_bytes + 256;
         };
         if (rt) {
             while (Br[2] > 4 && rt_need(Br[2]) > (size_t)(SMEM_PER_SM / 2 - 1024)) --Br[2];
@@ -525,7 +525,7 @@ void host_plan_free(Plan &p)
     p.d_uhat = nullptr;
     f(p.d_us); f(p.d_cs);
     for (int d = 0; d < 3; ++d) { f(p.d_phihat[d]); f(p.d_imap[d]); f(p.d_invmap[d]); f(p.d_xs[d]); }
-    f(p.d_keys[0]); f(p.d_keys[1]); f(p.d_vals[0]); f(p.d_vals[1]);
+    f(p.d_keys[0]); f(p.d_keys[1]); f(p.d_vals[0]); f(p.d_vals[1]); f(p.d_rec);
     f(p.d_perm_coarse);
     f(p.d_bin_offsets); f(p.d_hist); f(p.d_scan_tmp); f(p.d_item_start); f(p.d_item_table); f(p.d_counters);
     if (p.ev_ok) { for (int i = 0; i < 32; ++i) cudaEventDestroy(p.ev[i]); p.ev_ok = false; }

@@ -5,23 +5,25 @@
 // CTA = 4 independent warps sharing one read-only tile (the bin's padded subgrid, staged with cp.async), persistent,
 // pulling (bin, chunk) work items from a device counter.  Inside an item the warps pull 32-point batches from a
 // shared-memory counter; a batch never leaves its warp (no CTA barrier between tile loads):
-//   evaluate   one thread per point: x / y kernel values zero-padded to the column footprint, z values ROTATED so that
-//              the weight of tile plane z sits at index z & 7, and the (column, z) key -> the warp's private record
-//              buffer;
-//   accumulate lane L keeps its 4 footprint cells of the 8 planes [tz, tz + 8) in registers (plane z in register set
-//              z & 7).  Points arrive ordered by (column, z): when the window moves only the new planes are loaded.
-//              Per point: 6 shared-memory loads, 36 FFMA2 (packed re/im), then the 32 lane partials of 32 consecutive
-//              points are summed by a streaming butterfly transposition (31 exchanges per 32 points) that leaves
-//              point bitrev5(L) in lane L;
+//   evaluate   one thread per point: x / y / z kernel values zero-padded to the footprint of the point's 4 x 4 x 4-cell
+//              sub-bin (11 cells per dimension) -> the warp's private record buffer; the (column, z block) key stays in
+//              the lane's register;
+//   accumulate lane L keeps its 4 footprint cells of 12 planes in registers: three GROUPS of 4 planes, group g = planes
+//              4g .. 4g + 3 of the column, held in register group g % 3.  Points arrive ordered by (column, z): a run of
+//              points of the same (column, z block) is a branch-free loop of 6 shared-memory loads and 50 FFMA2 per
+//              point; moving to the next z block loads ONE new group (16 LDS.64).  The 32 lane partials of 32
+//              consecutive points are summed by a streaming butterfly transposition (31 exchanges per 32 points)
+//              that leaves point bitrev5(L) in lane L;
 //   store      prefactor, non-uniform callback, scatter through the permutation.
 #pragma once
+#include <type_traits>
 #include "rt_common.cuh"
 
 namespace nufft {
 namespace rt {
 
 constexpr int INTERP_NW = 4;
-constexpr int IOFF_WZ = 0, IOFF_KEY = 8;          // record: [0..7] rotated wz, [8] key, [16..39] wyT, [40..51] wx_pad
+constexpr int IOFF_WZ = 0;                        // record: [0..11] wz_pad, [16..39] wyT, [40..51] wx_pad
 constexpr int PLANE_IT = (23 * 23 + 31) / 32;     // cp.async per lane and tile plane (bins of 16 x 16 cells in x, y)
 
 __device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m)
@@ -137,6 +139,7 @@ rt_interp_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
                 const int32_t n_out = has_out ? a.perm[kb + brev] : 0;
 
                 // ---- evaluate: one thread per point -----------------------------------------------------------
+                int mykey = -1;                            // (column y << 12) | (column x << 8) | z block
                 if (lane < nb) {
                     float *r = rec_w + lane * REC_F;
                     float w[W], pw[P];
@@ -150,72 +153,89 @@ rt_interp_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
                     pad_shift(w, ty & 3, pw);
                     store_y(r, pw);
                     const int tz = eval_kernel_values<float, M>(kp, cs_s + 2 * kp.cs_stride, 2, z, w) - org2;
-#pragma unroll
-                    for (int j = 0; j < W; ++j) r[IOFF_WZ + ((tz + j) & 7)] = w[j];
-                    reinterpret_cast<int *>(r)[IOFF_KEY] = ((ty >> 2) << 12) | ((tx >> 2) << 8) | tz;
+                    pad_shift(w, tz & 3, pw);
+                    q = reinterpret_cast<float4 *>(r + IOFF_WZ);
+                    q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                    q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+                    q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
+                    mykey = ((ty >> 2) << 12) | ((tx >> 2) << 8) | (tz >> 2);
                 }
                 __syncwarp();
+                // runs of equal key: bit p of `starts` is set when point p opens a new (column, z block)
+                unsigned starts;
+                {
+                    const int prev = __shfl_up_sync(0xffffffffu, mykey, 1);
+                    starts = __ballot_sync(0xffffffffu, lane < nb && (lane == 0 || mykey != prev));
+                }
 
                 // ---- accumulate ---------------------------------------------------------------------------------
-                u64 G[8][NG];
+                u64 G[3][4][NG];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int g3 = 0; g3 < 3; ++g3)
 #pragma unroll
-                    for (int k = 0; k < NG; ++k) G[i][k] = 0ull;
-                int cur_col = -1, hi = 0;                 // planes [.., hi) of column cur_col are in registers
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < NG; ++k) G[g3][i][k] = 0ull;
                 u64 c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, res = 0;
                 const float *pY = rec_w + OFF_WY + 4 * ls.row, *pX = rec_w + OFF_WX + ls.x, *pX3 = rec_w + OFF_WX + ls.x3;
 
-                auto load_plane = [&](const Cell *cb, int zp) {
-                    const Cell *pl = cb + zp * S2;
-                    switch (zp & 7) {
-#define NUFFT_RT_SET(I)                                                                                       \
-    case I:                                                                                                   \
-        if constexpr (CPLX) {                                                                                 \
-            lds64_inplace(G[I][0], pl + off0); lds64_inplace(G[I][1], pl + off0 + 3 * Sx);                    \
-            lds64_inplace(G[I][2], pl + off0 + 6 * Sx); lds64_inplace(G[I][3], pl + off3);                    \
-        } else {                                                                                              \
-            lds32x2_inplace(G[I][0], pl + off0, pl + off0 + 3 * Sx);                                          \
-            lds32x2_inplace(G[I][1], pl + off0 + 6 * Sx, pl + off3);                                          \
-        }                                                                                                     \
-        break;
-                        NUFFT_RT_SET(0) NUFFT_RT_SET(1) NUFFT_RT_SET(2) NUFFT_RT_SET(3)
-                        NUFFT_RT_SET(4) NUFFT_RT_SET(5) NUFFT_RT_SET(6) NUFFT_RT_SET(7)
-#undef NUFFT_RT_SET
-                    }
-                };
-                auto xchg = [&](u64 ea, u64 la, int m) -> u64 {     // earlier point stays in lanes with bit m clear
+                // streaming butterfly: a binary counter of partial transposes (levels xor 16, 8, 4, 2, 1); the earlier
+                // point of a pair stays in the lanes whose bit is clear
+                auto xchg = [&](u64 ea, u64 la, int m) -> u64 {
                     const bool bit = (lane & m) != 0;
                     const u64 send = bit ? ea : la, keep = bit ? la : ea;
                     return fadd2(keep, shfl_xor_u64(send, m));
                 };
-
-                for (int p = 0; p < BATCH; ++p) {
-                    u64 v = 0ull;
-                    if (p < nb) {
+                auto bfly = [&](int p, u64 v) {
+                    if (!(p & 1)) { c0 = v; return; }
+                    v = xchg(c0, v, 16);
+                    if (!(p & 2)) { c1 = v; return; }
+                    v = xchg(c1, v, 8);
+                    if (!(p & 4)) { c2 = v; return; }
+                    v = xchg(c2, v, 4);
+                    if (!(p & 8)) { c3 = v; return; }
+                    v = xchg(c3, v, 2);
+                    if (!(p & 16)) { c4 = v; return; }
+                    res = xchg(c4, v, 1);
+                };
+                // group g of column base cb -> register group g % 3 (in-place loads keep the register state put)
+                auto load_group = [&](const Cell *cb, int g) {
+#define NUFFT_RT_LOADG(R3)                                                                                    \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                                           \
+        const Cell *pl = cb + min(4 * g + i, Tz - 1) * S2;                                                    \
+        if constexpr (CPLX) {                                                                                 \
+            lds64_inplace(G[R3][i][0], pl + off0); lds64_inplace(G[R3][i][1], pl + off0 + 3 * Sx);            \
+            lds64_inplace(G[R3][i][2], pl + off0 + 6 * Sx); lds64_inplace(G[R3][i][3], pl + off3);            \
+        } else {                                                                                              \
+            lds32x2_inplace(G[R3][i][0], pl + off0, pl + off0 + 3 * Sx);                                      \
+            lds32x2_inplace(G[R3][i][1], pl + off0 + 6 * Sx, pl + off3);                                      \
+        }                                                                                                     \
+    }
+                    const int r3 = g % 3;
+                    if (r3 == 0) { NUFFT_RT_LOADG(0) } else if (r3 == 1) { NUFFT_RT_LOADG(1) } else { NUFFT_RT_LOADG(2) }
+#undef NUFFT_RT_LOADG
+                };
+                // points [p0, p1) share the window: plane i of the window = register group (ROT + i / 4) % 3, plane i % 4
+                auto run = [&](auto rot, int p0, int p1) {
+                    constexpr int ROT = decltype(rot)::value;
+                    for (int p = p0; p < p1; ++p) {
                         const float *r = rec_w + p * REC_F;
-                        const int key = reinterpret_cast<const int *>(r)[IOFF_KEY];
                         const float4 za = *reinterpret_cast<const float4 *>(r + IOFF_WZ);
                         const float4 zb = *reinterpret_cast<const float4 *>(r + IOFF_WZ + 4);
+                        const float4 zc = *reinterpret_cast<const float4 *>(r + IOFF_WZ + 8);
                         const float4 wy = *reinterpret_cast<const float4 *>(pY + p * REC_F);
                         const float wx = pX[p * REC_F], wx3 = pX3[p * REC_F];
-                        const int col = key >> 8, tz = key & 0xff;
-                        if (col != cur_col) { cur_col = col; hi = 0; }
-                        if (hi < tz + 8) {
-                            const Cell *cb = tile + (4 * (col >> 4)) * Sx + 4 * (col & 15);
-                            for (int zp = max(hi, tz); zp < tz + 8; ++zp) load_plane(cb, zp);
-                            hi = tz + 8;
-                        }
-                        const float wz[8] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w};
+                        const float wz[11] = {za.x, za.y, za.z, za.w, zb.x, zb.y, zb.z, zb.w, zc.x, zc.y, zc.z};
                         u64 h[NG];
 #pragma unroll
-                        for (int k = 0; k < NG; ++k) h[k] = fmul2(pk2(wz[0], wz[0]), G[0][k]);
+                        for (int k = 0; k < NG; ++k) h[k] = fmul2(pk2(wz[0], wz[0]), G[ROT % 3][0][k]);
 #pragma unroll
-                        for (int i = 1; i < 8; ++i)
+                        for (int i = 1; i < 11; ++i)
 #pragma unroll
-                            for (int k = 0; k < NG; ++k) h[k] = ffma2(pk2(wz[i], wz[i]), G[i][k], h[k]);
+                            for (int k = 0; k < NG; ++k) h[k] = ffma2(pk2(wz[i], wz[i]), G[(ROT + i / 4) % 3][i % 4][k], h[k]);
                         const u64 w01 = fmul2(pk2(wx, wx), pk2(wy.x, wy.y));
                         const u64 w23 = fmul2(pk2(wx, wx3), pk2(wy.z, wy.w));
+                        u64 v;
                         if constexpr (CPLX) {
                             const float2 wa = unpk2(w01), wb = unpk2(w23);
                             v = fmul2(pk2(wa.x, wa.x), h[0]);
@@ -225,19 +245,29 @@ rt_interp_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
                         } else {
                             v = ffma2(w23, h[1], fmul2(w01, h[0]));      // (slots 0 + 2, slots 1 + 3): summed at the end
                         }
+                        bfly(p, v);
                     }
-                    // streaming butterfly: a binary counter of partial transposes (levels xor 16, 8, 4, 2, 1)
-                    if (!(p & 1)) { c0 = v; continue; }
-                    v = xchg(c0, v, 16);
-                    if (!(p & 2)) { c1 = v; continue; }
-                    v = xchg(c1, v, 8);
-                    if (!(p & 4)) { c2 = v; continue; }
-                    v = xchg(c2, v, 4);
-                    if (!(p & 8)) { c3 = v; continue; }
-                    v = xchg(c3, v, 2);
-                    if (!(p & 16)) { c4 = v; continue; }
-                    res = xchg(c4, v, 1);
+                };
+
+                int cur_col = -1, hi_g = 0;               // groups [.., hi_g) of column cur_col are in registers
+                for (int p0 = 0; p0 < nb;) {
+                    const unsigned rest = starts & ~((2u << p0) - 1u);       // run starts after p0
+                    const int p1 = rest ? __ffs(rest) - 1 : nb;
+                    const int key = __shfl_sync(0xffffffffu, mykey, p0);
+                    const int col = key >> 8, zb = key & 0xff;
+                    if (col != cur_col) { cur_col = col; hi_g = 0; }
+                    {
+                        const Cell *cb = tile + (4 * (col >> 4)) * Sx + 4 * (col & 15);
+                        for (int g = max(hi_g, zb); g < zb + 3; ++g) load_group(cb, g);
+                        hi_g = zb + 3;
+                    }
+                    const int r3 = zb % 3;
+                    if (r3 == 0) run(std::integral_constant<int, 0>{}, p0, p1);
+                    else if (r3 == 1) run(std::integral_constant<int, 1>{}, p0, p1);
+                    else run(std::integral_constant<int, 2>{}, p0, p1);
+                    p0 = p1;
                 }
+                for (int p = nb; p < BATCH; ++p) bfly(p, 0ull);      // partial batch: complete the transposition
                 // ---- store -----------------------------------------------------------------------------------------
                 if (has_out) {
                     const float2 rv = unpk2(res);

@@ -2,21 +2,23 @@
 //
 // Replaces src/spreading/gpu.jl:237-434 for this configuration class (same sums, different order).
 //
-// CTA = 4 warps, persistent, pulling (bin, chunk) work items from a device counter.  set_points has ordered the points
-// of a bin by (4 x 4-cell column, z cell), so consecutive points share their padded (x, y) footprint of 11 x 11 cells
-// and move monotonically along z.
-//   evaluate  : every warp first evaluates ONE ingredient of the next 32-point batch, one thread per point —
-//               warp 0 the x weights, warp 1 the y weights (both zero-padded to the column footprint), warp 2 the z
-//               weights times the point's value, warp 3 the column / plane keys — into a double-buffered record
-//               (one CTA barrier per batch; coordinates, permutation and values are prefetched one batch ahead);
-//   accumulate: warp w owns the tile planes z = w (mod 4).  A point's 8 planes meet every class exactly twice, so
-//               every warp does the same work for every point (no imbalance, one owner per cell, no shared-memory
-//               atomics).  The two planes live in REGISTERS (plane q of the class in the even / odd accumulator set by
-//               parity of q): per point and warp 5 shared-memory loads, 2 FMUL2 and 8 FFMA2 (packed re/im) and no
-//               tile traffic.  Because z only grows inside a column, a plane is read-modified-written to the tile
-//               exactly once per column, when the window moves past it;
-//   flush     : tile -> oversampled grid with red.global.add.v4.f32 (2 complex cells), as spread_sm_kernel.
+// CTA = 4 independent warps sharing one tile (the bin's padded subgrid in shared memory), persistent, pulling
+// (bin, chunk) work items from a device counter.  Inside an item the warps pull 32-point batches from a shared-memory
+// counter; a batch never leaves its warp (CTA barriers only around the tile flush):
+//   evaluate   one thread per point: x / y kernel values zero-padded to the footprint of the point's 4 x 4 x 4-cell
+//              sub-bin (11 cells per dimension), z values likewise and multiplied by the point's value -> the warp's
+//              private record buffer; the (column, z block) key stays in the lane's register;
+//   accumulate lane L keeps its 4 footprint cells of 12 planes in REGISTERS: three groups of 4 planes, group g = planes
+//              4g .. 4g + 3 of the column in register group g % 3.  Points arrive ordered by (column, z): a run of points
+//              of the same (column, z block) is a branch-free loop of 9 shared-memory loads and 46 FFMA2 / FMUL2
+//              (packed re/im) per point and touches no tile memory;
+//   retire     when the window moves on, the group that falls out is added to the tile.  Warps work on different
+//              columns whose footprints overlap, so the add is a 64-bit compare-and-swap loop on the (re, im) cell
+//              (shared memory has no native floating-point atomics); it runs once per (column, plane), not per point;
+//   flush      tile -> oversampled grid with red.global.add.v4.f32 (2 complex cells); every lane owns a fixed set of
+//              16-byte vectors of the flattened (x, y) plane, so a plane costs 9 loads + reductions per lane.
 #pragma once
+#include <type_traits>
 #include "rt_common.cuh"
 #include "spread.cuh"
 
@@ -24,6 +26,32 @@ namespace nufft {
 namespace rt {
 
 constexpr int SPREAD_NWARP = 4;
+// record (floats): [0..23] value x wz_pad (complex: 11 x (re, im) + pad; real: 11 + pad), [24..47] wyT, [48..59] wx_pad
+constexpr int SREC_F = RT_SREC_F;
+constexpr int SOFF_S = 0, SOFF_WY = 24, SOFF_WX = 48;
+constexpr int FLJ = 10;            // 16-byte vectors per lane and tile plane in the flush (23 rows x <= 13 vectors / 32)
+
+// cell += v in shared memory, safe against concurrent adders
+__device__ __forceinline__ void smem_add(float2 *cell, u64 v)
+{
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(cell);
+    u64 old = *a;
+    while (true) {
+        const u64 prev = atomicCAS(a, old, fadd2(old, v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
+__device__ __forceinline__ void smem_add(float *cell, float v)
+{
+    int *a = reinterpret_cast<int *>(cell);
+    int old = *a;
+    while (true) {
+        const int prev = atomicCAS(a, old, __float_as_int(__int_as_float(old) + v));
+        if (prev == old) break;
+        old = prev;
+    }
+}
 
 template <bool CPLX>
 __global__ void __launch_bounds__(32 * SPREAD_NWARP, 2)
@@ -35,18 +63,20 @@ rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
     constexpr int NWARP = SPREAD_NWARP;
     constexpr int NT = 32 * NWARP;
     constexpr int VEC = FlushVec<Cell>::VEC;
+    constexpr int NG = CPLX ? 4 : 2;               // u64 registers per plane: complex (re, im) per slot; real (slot k, k + 1)
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tile_bytes = (g.tile_cells * (int)sizeof(Cell) + 15) & ~15;
     Cell *tile = (Cell *)smem_raw;
-    float *rec_s = (float *)(smem_raw + tile_bytes);                  // [2][BATCH][REC_F]
-    int *key_s = (int *)(rec_s + 2 * BATCH * REC_F);                  // [2][BATCH][4]
-    float *cs_s = (float *)(key_s + 2 * BATCH * 4);                   // [3][cs_stride]
+    float *rec_all = (float *)(smem_raw + tile_bytes);                // [NWARP][BATCH][SREC_F]
+    float *cs_s = rec_all + NWARP * BATCH * SREC_F;                   // [3][cs_stride]
     __shared__ int s_item[2][4];
+    __shared__ int s_batch;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Tx = g.T[0], Ty = g.T[1], Tz = g.T[2], Sx = g.S[0], S2 = g.S[2];
     const int total_items = a.item_start[a.nbins];
+    float *rec_w = rec_all + warp * BATCH * SREC_F;
 
     const LaneSlots ls = lane_slots(lane);
     const int off0 = ls.g * Sx + ls.x, off3 = ls.y3 * Sx + ls.x3;     // slot k < 3: off0 + 3 k Sx
@@ -60,13 +90,18 @@ rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
         const int item = atomicAdd(a.work_counter, 1);
         s_item[0][0] = item;
         if (item < total_items) decode_item(a, item, g.chunk, s_item[0][1], s_item[0][2], s_item[0][3]);
+        s_batch = 0;
     }
     __syncthreads();
 
-    // register window of this warp: even / odd plane of its class; CPLX: (re, im) per slot, real: (even, odd) per slot
-    u64 accE[4], accO[4];
+    // register window: three groups of four planes
+    u64 G[3][4][NG];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { accE[k] = 0ull; accO[k] = 0ull; }
+    for (int g3 = 0; g3 < 3; ++g3)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < NG; ++k) G[g3][i][k] = 0ull;
 
     for (int it = 0;; ++it) {
         const int *cur = s_item[it & 1];
@@ -86,226 +121,221 @@ rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
         const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
 
         for (int c = 0; c < C; ++c) {
-            // ---- evaluation role of this warp (one thread per point of the batch) ------------------------------
-            // register prefetch: coordinates of this lane's point in the NEXT batch to evaluate; warp 2 also its value
-            // (vp[perm[k]] is two dependent loads: the permutation entry is fetched one batch earlier still)
-            float xq = 0.f, yq = 0.f, zq = 0.f;
-            Cell vq = cell_zero((Cell *)nullptr);
-            int32_t nq = 0;
             auto load_v = [&](int32_t n) -> Cell {
                 Cell v = load_value<float, CPLX>(vp.p[c], n);
                 if (nu_weights) v = cmul(v, nu_weights[n]);
                 return v;
             };
-            auto prefetch = [&](int k) {
-                if (k < k1) {
-                    if (warp == 0 || warp == 3) xq = xs0[k];
-                    if (warp == 1 || warp == 3) yq = xs1[k];
-                    if (warp >= 2) zq = xs2[k];
-                    if (warp == 2) vq = load_v(nq);
-                }
-                if (warp == 2 && k + BATCH < k1) nq = a.perm[k + BATCH];
-            };
-            if (warp == 2 && k0 + lane < k1) nq = a.perm[k0 + lane];
-            prefetch(k0 + lane);
-
-            auto produce = [&](int bi) {
+            // ---- batches of this item, pulled by the warps; coordinates / values of the next batch are prefetched ----
+            int bi = 0;
+            if (lane == 0) bi = atomicAdd(&s_batch, 1);
+            bi = __shfl_sync(0xffffffffu, bi, 0);
+            float xq = 0.f, yq = 0.f, zq = 0.f;
+            Cell vq = cell_zero((Cell *)nullptr);
+            {
+                const int k = k0 + bi * BATCH + lane;
+                if (bi < nbatches && k < k1) { xq = xs0[k]; yq = xs1[k]; zq = xs2[k]; vq = load_v(a.perm[k]); }
+            }
+            while (bi < nbatches) {
                 const int kb = k0 + bi * BATCH;
                 const int nb = min(BATCH, k1 - kb);
-                float *r = rec_s + ((bi & 1) * BATCH + lane) * REC_F;
+                int bn = 0;
+                if (lane == 0) bn = atomicAdd(&s_batch, 1);
+                bn = __shfl_sync(0xffffffffu, bn, 0);
                 const float x = xq, y = yq, z = zq;
                 const Cell v = vq;
-                prefetch(kb + BATCH + lane);          // loads of the following batch fly during this evaluation
-                if (lane < nb) {
-                    float w[W], pw[P];
-                    if (warp == 0) {
-                        const int tx = eval_kernel_values<float, M>(kp, cs_s, 0, x, w) - org0;
-                        pad_shift(w, tx & 3, pw);
-                        float4 *q = reinterpret_cast<float4 *>(r + OFF_WX);
-                        q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
-                        q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
-                        q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
-                    } else if (warp == 1) {
-                        const int ty = eval_kernel_values<float, M>(kp, cs_s + kp.cs_stride, 1, y, w) - org1;
-                        pad_shift(w, ty & 3, pw);
-                        store_y(r, pw);
-                    } else if (warp == 2) {
-                        const int tz = eval_kernel_values<float, M>(kp, cs_s + 2 * kp.cs_stride, 2, z, w) - org2;
-                        // planes tz + j, j = 0..7: class (tz + j) & 3 owns j and j + 4; the one whose class-plane
-                        // index q = (tz + j) >> 2 is even goes to the even accumulator
-                        float4 *s4 = reinterpret_cast<float4 *>(r + OFF_S);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int t = tz + j;
-                            const bool odd = ((t >> 2) & 1) != 0;
-                            const float we = odd ? w[j + 4] : w[j], wo = odd ? w[j] : w[j + 4];
-                            if constexpr (CPLX) s4[t & 3] = make_float4(v.x * we, v.y * we, v.x * wo, v.y * wo);
-                            else s4[t & 3] = make_float4(v * we, v * wo, 0.f, 0.f);
-                        }
-                    } else {
-                        float rr;
-                        const int tx = point_to_cell0<float>(x, kp.N[0], rr) - org0;
-                        const int ty = point_to_cell0<float>(y, kp.N[1], rr) - org1;
-                        const int tz = point_to_cell0<float>(z, kp.N[2], rr) - org2;
-                        const int col = (((ty >> 2) << 4) | (tx >> 2)) << 8;
-                        // first plane index of class c touched by the support: q = ceil((tz - c) / 4)
-                        reinterpret_cast<int4 *>(key_s)[(bi & 1) * BATCH + lane] =
-                            make_int4(col | ((tz + 3) >> 2), col | ((tz + 2) >> 2), col | ((tz + 1) >> 2), col | (tz >> 2));
-                    }
-                }
-            };
-
-            // ---- accumulate: add the even / odd register plane to the tile, clear it ---------------------------
-            auto retire = [&](u64 (&acc)[4], int col, int q) {
-                const int t = warp + 4 * q;
-                if (t < Tz) {
-                    Cell *pl = tile + (4 * ((col >> 4) & 15)) * Sx + 4 * (col & 15) + t * S2;
-                    if constexpr (CPLX) {
-                        float2 t0 = pl[off0], t1 = pl[off0 + 3 * Sx], t2 = pl[off0 + 6 * Sx], t3 = pl[off3];
-                        const float2 a0 = unpk2(acc[0]), a1 = unpk2(acc[1]), a2 = unpk2(acc[2]), a3 = unpk2(acc[3]);
-                        t0.x += a0.x; t0.y += a0.y; t1.x += a1.x; t1.y += a1.y;
-                        t2.x += a2.x; t2.y += a2.y; t3.x += a3.x; t3.y += a3.y;
-                        pl[off0] = t0; pl[off0 + 3 * Sx] = t1; pl[off0 + 6 * Sx] = t2;
-                        if (ls.has3) pl[off3] = t3;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) zero_inplace(acc[k]);
-            };
-            // real data: both planes share the accumulators (even, odd) -> one combined retire
-            auto retire_real = [&](int col, int cqa, bool doE, bool doO) {
-                if constexpr (!CPLX) {
-                    const int qe = (cqa + 1) & ~1, qo = cqa | 1;
-                    Cell *base = tile + (4 * ((col >> 4) & 15)) * Sx + 4 * (col & 15);
-                    float e[4], o[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { const float2 t = unpk2(accE[k]); e[k] = t.x; o[k] = t.y; }
-                    const int te = warp + 4 * qe, to = warp + 4 * qo;
-                    if (doE && te < Tz) {
-                        Cell *pl = base + te * S2;
-                        pl[off0] += e[0]; pl[off0 + 3 * Sx] += e[1]; pl[off0 + 6 * Sx] += e[2];
-                        if (ls.has3) pl[off3] += e[3];
-                    }
-                    if (doO && to < Tz) {
-                        Cell *pl = base + to * S2;
-                        pl[off0] += o[0]; pl[off0 + 3 * Sx] += o[1]; pl[off0 + 6 * Sx] += o[2];
-                        if (ls.has3) pl[off3] += o[3];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) accE[k] = pk2(doE ? 0.f : e[k], doO ? 0.f : o[k]);
-                }
-            };
-            int cur_key = -1;
-            auto window_move = [&](int key) {          // key < 0: retire everything
-                if (cur_key >= 0) {
-                    const int ccol = cur_key >> 8, cqa = cur_key & 0xff;
-                    const bool all = key < 0 || (key >> 8) != ccol || (key & 0xff) - cqa >= 2;
-                    const bool doE = all || !(cqa & 1), doO = all || (cqa & 1);
-                    if constexpr (CPLX) {
-                        if (doE) retire(accE, ccol, (cqa + 1) & ~1);
-                        if (doO) retire(accO, ccol, cqa | 1);
-                    } else {
-                        retire_real(ccol, cqa, doE, doO);
-                    }
-                }
-                cur_key = key;
-            };
-
-            produce(0);
-            __syncthreads();
-            for (int bi = 0; bi < nbatches; ++bi) {
-                if (bi + 1 < nbatches) produce(bi + 1);
                 {
-                    const int nb = min(BATCH, k1 - (k0 + bi * BATCH));
-                    const float *r = rec_s + (bi & 1) * BATCH * REC_F;
-                    const float *pS = r + OFF_S + 4 * warp, *pY = r + OFF_WY + 4 * ls.row;
-                    const float *pX = r + OFF_WX + ls.x, *pX3 = r + OFF_WX + ls.x3;
-                    const int *pK = key_s + (bi & 1) * BATCH * 4 + warp;
-                    // software pipeline: the record of point p + 1 is loaded while point p is accumulated
-                    float4 s = *reinterpret_cast<const float4 *>(pS);
-                    float4 wy = *reinterpret_cast<const float4 *>(pY);
-                    float wx = *pX, wx3 = *pX3;
-                    int key = *pK;
-#pragma unroll 2
-                    for (int p = 0; p < nb; ++p) {
-                        const int on = min(p + 1, nb - 1);
-                        const float4 s_n = *reinterpret_cast<const float4 *>(pS + on * REC_F);
-                        const float4 wy_n = *reinterpret_cast<const float4 *>(pY + on * REC_F);
-                        const float wx_n = pX[on * REC_F], wx3_n = pX3[on * REC_F];
-                        const int key_n = pK[on * 4];
+                    const int k = k0 + bn * BATCH + lane;
+                    if (bn < nbatches && k < k1) { xq = xs0[k]; yq = xs1[k]; zq = xs2[k]; vq = load_v(a.perm[k]); }
+                }
 
-                        if (key != cur_key) window_move(key);
+                // ---- evaluate: one thread per point -----------------------------------------------------------
+                int mykey = -1;                            // (column y << 12) | (column x << 8) | z block
+                if (lane < nb) {
+                    float *r = rec_w + lane * SREC_F;
+                    float w[W], pw[P];
+                    const int tx = eval_kernel_values<float, M>(kp, cs_s, 0, x, w) - org0;
+                    pad_shift(w, tx & 3, pw);
+                    float4 *q = reinterpret_cast<float4 *>(r + SOFF_WX);
+                    q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                    q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+                    q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
+                    const int ty = eval_kernel_values<float, M>(kp, cs_s + kp.cs_stride, 1, y, w) - org1;
+                    pad_shift(w, ty & 3, pw);
+                    store_y(r + (SOFF_WY - OFF_WY), pw);
+                    const int tz = eval_kernel_values<float, M>(kp, cs_s + 2 * kp.cs_stride, 2, z, w) - org2;
+                    pad_shift(w, tz & 3, pw);
+                    q = reinterpret_cast<float4 *>(r + SOFF_S);
+                    if constexpr (CPLX) {
+#pragma unroll
+                        for (int i = 0; i < 5; ++i)
+                            q[i] = make_float4(v.x * pw[2 * i], v.y * pw[2 * i], v.x * pw[2 * i + 1], v.y * pw[2 * i + 1]);
+                        q[5] = make_float4(v.x * pw[10], v.y * pw[10], 0.f, 0.f);
+                    } else {
+                        q[0] = make_float4(v * pw[0], v * pw[1], v * pw[2], v * pw[3]);
+                        q[1] = make_float4(v * pw[4], v * pw[5], v * pw[6], v * pw[7]);
+                        q[2] = make_float4(v * pw[8], v * pw[9], v * pw[10], 0.f);
+                    }
+                    mykey = ((ty >> 2) << 12) | ((tx >> 2) << 8) | (tz >> 2);
+                }
+                __syncwarp();
+                // runs of equal key: bit p of `starts` is set when point p opens a new (column, z block)
+                unsigned starts;
+                {
+                    const int prev = __shfl_up_sync(0xffffffffu, mykey, 1);
+                    starts = __ballot_sync(0xffffffffu, lane < nb && (lane == 0 || mykey != prev));
+                }
+
+                // ---- accumulate ---------------------------------------------------------------------------------
+                const float *pY = rec_w + SOFF_WY + 4 * ls.row, *pX = rec_w + SOFF_WX + ls.x, *pX3 = rec_w + SOFF_WX + ls.x3;
+                // add register group g % 3 (= planes 4g .. 4g + 3 of column base cb) to the tile and clear it
+                auto retire_group = [&](Cell *cb, int gq) {
+#define NUFFT_RT_RETIRE(R3)                                                                                   \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) {                                                           \
+        const int zp = 4 * gq + i;                                                                            \
+        if (zp < Tz) {                                                                                        \
+            Cell *pl = cb + zp * S2;                                                                          \
+            if constexpr (CPLX) {                                                                             \
+                smem_add(pl + off0, G[R3][i][0]); smem_add(pl + off0 + 3 * Sx, G[R3][i][1]);                  \
+                smem_add(pl + off0 + 6 * Sx, G[R3][i][2]);                                                    \
+                if (ls.has3) smem_add(pl + off3, G[R3][i][3]);                                                \
+            } else {                                                                                          \
+                const float2 ta = unpk2(G[R3][i][0]), tb = unpk2(G[R3][i][1]);                                \
+                smem_add(pl + off0, ta.x); smem_add(pl + off0 + 3 * Sx, ta.y);                                \
+                smem_add(pl + off0 + 6 * Sx, tb.x);                                                           \
+                if (ls.has3) smem_add(pl + off3, tb.y);                                                       \
+            }                                                                                                 \
+        }                                                                                                     \
+        _Pragma("unroll") for (int k = 0; k < NG; ++k) zero_inplace(G[R3][i][k]);                             \
+    }
+                    const int r3 = gq % 3;
+                    if (r3 == 0) { NUFFT_RT_RETIRE(0) } else if (r3 == 1) { NUFFT_RT_RETIRE(1) } else { NUFFT_RT_RETIRE(2) }
+#undef NUFFT_RT_RETIRE
+                };
+                // points [p0, p1) share the window: plane i of the window = register group (ROT + i / 4) % 3, plane i % 4
+                auto run = [&](auto rot, int p0, int p1) {
+                    constexpr int ROT = decltype(rot)::value;
+                    for (int p = p0; p < p1; ++p) {
+                        const float *r = rec_w + p * SREC_F;
+                        const float4 wy = *reinterpret_cast<const float4 *>(pY + p * SREC_F);
+                        const float wx = pX[p * SREC_F], wx3 = pX3[p * SREC_F];
                         const u64 w01 = fmul2(pk2(wx, wx), pk2(wy.x, wy.y));
                         const u64 w23 = fmul2(pk2(wx, wx3), pk2(wy.z, wy.w));
-                        const float2 wa = unpk2(w01), wb = unpk2(w23);
                         if constexpr (CPLX) {
-                            const u64 sE = pk2(s.x, s.y), sO = pk2(s.z, s.w);
-                            accE[0] = ffma2(pk2(wa.x, wa.x), sE, accE[0]);
-                            accE[1] = ffma2(pk2(wa.y, wa.y), sE, accE[1]);
-                            accE[2] = ffma2(pk2(wb.x, wb.x), sE, accE[2]);
-                            accE[3] = ffma2(pk2(wb.y, wb.y), sE, accE[3]);
-                            accO[0] = ffma2(pk2(wa.x, wa.x), sO, accO[0]);
-                            accO[1] = ffma2(pk2(wa.y, wa.y), sO, accO[1]);
-                            accO[2] = ffma2(pk2(wb.x, wb.x), sO, accO[2]);
-                            accO[3] = ffma2(pk2(wb.y, wb.y), sO, accO[3]);
+                            const float2 wa = unpk2(w01), wb = unpk2(w23);
+                            const float4 *sq = reinterpret_cast<const float4 *>(r + SOFF_S);
+#pragma unroll
+                            for (int h = 0; h < 6; ++h) {
+                                const float4 s2 = sq[h];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int i = 2 * h + e;
+                                    if (i < 11) {
+                                        const u64 sv = e == 0 ? pk2(s2.x, s2.y) : pk2(s2.z, s2.w);
+                                        u64(&acc)[NG] = G[(ROT + i / 4) % 3][i % 4];
+                                        acc[0] = ffma2(pk2(wa.x, wa.x), sv, acc[0]);
+                                        acc[1] = ffma2(pk2(wa.y, wa.y), sv, acc[1]);
+                                        acc[2] = ffma2(pk2(wb.x, wb.x), sv, acc[2]);
+                                        acc[3] = ffma2(pk2(wb.y, wb.y), sv, acc[3]);
+                                    }
+                                }
+                            }
                         } else {
-                            const u64 sEO = pk2(s.x, s.y);
-                            accE[0] = ffma2(pk2(wa.x, wa.x), sEO, accE[0]);
-                            accE[1] = ffma2(pk2(wa.y, wa.y), sEO, accE[1]);
-                            accE[2] = ffma2(pk2(wb.x, wb.x), sEO, accE[2]);
-                            accE[3] = ffma2(pk2(wb.y, wb.y), sEO, accE[3]);
+                            const float4 *sq = reinterpret_cast<const float4 *>(r + SOFF_S);
+                            const float4 sa = sq[0], sb = sq[1], sc = sq[2];
+                            const float sv[11] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, sc.x, sc.y, sc.z};
+#pragma unroll
+                            for (int i = 0; i < 11; ++i) {
+                                u64(&acc)[NG] = G[(ROT + i / 4) % 3][i % 4];
+                                acc[0] = ffma2(w01, pk2(sv[i], sv[i]), acc[0]);
+                                acc[1] = ffma2(w23, pk2(sv[i], sv[i]), acc[1]);
+                            }
                         }
-                        s = s_n; wy = wy_n; wx = wx_n; wx3 = wx3_n; key = key_n;
                     }
+                };
+
+                int cur_col = -1, lo_g = 0;               // register groups hold groups [lo_g, lo_g + 3) of column cur_col
+                Cell *cur_cb = tile;
+                for (int p0 = 0; p0 < nb;) {
+                    const unsigned rest = starts & ~((2u << p0) - 1u);       // run starts after p0
+                    const int p1 = rest ? __ffs(rest) - 1 : nb;
+                    const int key = __shfl_sync(0xffffffffu, mykey, p0);
+                    const int col = key >> 8, zb = key & 0xff;
+                    if (col != cur_col) {
+                        if (cur_col >= 0)
+                            for (int gq = lo_g; gq < lo_g + 3; ++gq) retire_group(cur_cb, gq);
+                        cur_col = col;
+                        cur_cb = tile + (4 * (col >> 4)) * Sx + 4 * (col & 15);
+                        lo_g = zb;
+                    } else if (zb > lo_g) {                // z only grows inside a column
+                        for (int gq = lo_g; gq < min(zb, lo_g + 3); ++gq) retire_group(cur_cb, gq);
+                        lo_g = zb;
+                    }
+                    const int r3 = zb % 3;
+                    if (r3 == 0) run(std::integral_constant<int, 0>{}, p0, p1);
+                    else if (r3 == 1) run(std::integral_constant<int, 1>{}, p0, p1);
+                    else run(std::integral_constant<int, 2>{}, p0, p1);
+                    p0 = p1;
                 }
-                __syncthreads();
+                if (cur_col >= 0)
+                    for (int gq = lo_g; gq < lo_g + 3; ++gq) retire_group(cur_cb, gq);
+                __syncwarp();
+                bi = bn;
             }
-            window_move(-1);
             __syncthreads();
+            if (tid == 0) s_batch = 0;             // every warp is done pulling batches; ordered by the barrier after the flush
             // ---- flush: tile -> global grid (periodic), vector reductions; re-zero the tile ------------
             {
                 Cell *u = us + (int64_t)c * ncells;
                 const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
                 const int x0 = org0 - (M - 1), y0 = org1 - (M - 1), z0 = org2 - (M - 1);
                 const Cell zero = cell_zero((Cell *)nullptr);
-                const bool vec_ok = (Nx % VEC) == 0;
-                const int hl = lane & 15, hrow = lane >> 4;
-                if (vec_ok) {
-                    const int a0 = pmod(x0, VEC);                  // tile x of vector q starts at VEC * q - a0
-                    const int nvec = (Tx + a0 + VEC - 1) / VEC;
-                    for (int qb = 0; qb < nvec; qb += 16) {
-                        const int q = qb + hl;
-                        const int xt = VEC * q - a0;
-                        const int gx = wrap1(x0 + xt, Nx);
-                        bool in[VEC];
+                const bool vec_ok = (Nx % VEC) == 0 && VEC > 1;
+                const int a0 = vec_ok ? pmod(x0, VEC) : 0;     // tile x of vector q starts at VEC * q - a0
+                const int nvec = (Tx + a0 + VEC - 1) / VEC;
+                if (vec_ok && Ty * nvec <= 32 * FLJ) {
+                    // lane-owned vectors of the flattened (row, vector) plane: offsets are computed once per item
+                    int soff[FLJ], goff[FLJ];
+                    unsigned long long inmask = 0;             // VEC bits per vector: cell inside the tile row
 #pragma unroll
-                        for (int e = 0; e < VEC; ++e) in[e] = q < nvec && xt + e >= 0 && xt + e < Tx;
-                        for (int z = 0; z < Tz; ++z) {
-                            const int gz = wrap1(z0 + z, Nz);
-                            Cell *gplane = u + (int64_t)gz * Ny * Nx + gx;
-                            Cell *tplane = tile + z * S2 + xt;
-                            for (int y = 2 * warp + hrow; y < Ty; y += 2 * NWARP) {
-                                const int gy = wrap1(y0 + y, Ny);
-                                Cell *trow = tplane + y * Sx;
+                    for (int j = 0; j < FLJ; ++j) {
+                        const int f = lane + 32 * j;
+                        const int y = f / nvec, q = f - y * nvec;
+                        const int xt = VEC * q - a0;
+                        soff[j] = y * Sx + xt;
+                        goff[j] = -1;
+                        if (y < Ty) {
+                            goff[j] = wrap1(y0 + y, Ny) * Nx + wrap1(x0 + xt, Nx);
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e)
+                                if (xt + e >= 0 && xt + e < Tx) inmask |= 1ull << (VEC * j + e);
+                        }
+                    }
+                    for (int zp = warp; zp < Tz; zp += NWARP) {
+                        Cell *gplane = u + (int64_t)wrap1(z0 + zp, Nz) * Ny * Nx;
+                        Cell *tplane = tile + zp * S2;
+#pragma unroll
+                        for (int j = 0; j < FLJ; ++j) {
+                            if (goff[j] >= 0) {
                                 Cell val[VEC];
                                 bool nz = false;
 #pragma unroll
                                 for (int e = 0; e < VEC; ++e) {
                                     val[e] = zero;
-                                    if (in[e]) { val[e] = trow[e]; trow[e] = zero; }
+                                    if ((inmask >> (VEC * j + e)) & 1ull) { val[e] = tplane[soff[j] + e]; tplane[soff[j] + e] = zero; }
                                     nz = nz || cnonzero(val[e]);
                                 }
-                                if (nz) red_vec(gplane + (int64_t)gy * Nx, val);
+                                if (nz) red_vec(gplane + goff[j], val);
                             }
                         }
                     }
                 } else {
-                    for (int z = 0; z < Tz; ++z) {
-                        const int gz = wrap1(z0 + z, Nz);
+                    for (int zp = 0; zp < Tz; ++zp) {
+                        const int gz = wrap1(z0 + zp, Nz);
                         for (int y = warp; y < Ty; y += NWARP) {
                             const int gy = wrap1(y0 + y, Ny);
                             Cell *grow = u + ((int64_t)gz * Ny + gy) * Nx;
-                            Cell *trow = tile + z * S2 + y * Sx;
+                            Cell *trow = tile + zp * S2 + y * Sx;
                             for (int x = lane; x < Tx; x += 32) {
                                 const Cell val = trow[x];
                                 trow[x] = zero;
@@ -323,8 +353,7 @@ rt_spread_kernel(KernelParams<float> kp, TileGeom g, SmArgs a, const float *__re
 inline size_t spread_smem_bytes(const TileGeom &g, int cs_stride, size_t cell_bytes)
 {
     size_t b = ((size_t)g.tile_cells * cell_bytes + 15) & ~(size_t)15;
-    b += (size_t)2 * BATCH * REC_F * sizeof(float);
-    b += (size_t)2 * BATCH * 4 * sizeof(int);
+    b += (size_t)SPREAD_NWARP * BATCH * SREC_F * sizeof(float);
     b += (size_t)(3 * cs_stride + 4) * sizeof(float);
     return b + 16;
 }
