@@ -116,6 +116,11 @@ int  nufft_plan_kernel_info(nufft_plan plan, int32_t d, double *shape_param, dou
 
 /* ---- set_points!(p, (xs, ys, zs)): src/set_points.jl:33-52 + src/blocking/gpu.jl:73-142 ---- */
 int  nufft_set_points(nufft_plan plan, int64_t np, const void *const x[/*dim*/]);
+/* set_points!(p, xp::AbstractMatrix) with size(xp) == (D, Np) and set_points!(p, xp::AbstractVector{<:SVector{D}})
+ * (src/set_points.jl:62-88; the reference copies both into D separate vectors on the host side of Julia): xmat is a
+ * dense column-major (D, Np) device matrix of the plan's real type, i.e. an array of Np D-vectors.  Read in place by
+ * the binning kernel — no transposed copy.  Same retention rules as nufft_set_points. */
+int  nufft_set_points_matrix(nufft_plan plan, int64_t np, const void *xmat);
 
 /* binning result (BlockDataGPU.pointperm / cumulative_npoints_per_block, src/blocking/gpu.jl:2-21).
  * Device pointers owned by the plan, valid until the next set_points / destroy. */

@@ -9,10 +9,12 @@ from .plan import (ArgumentError, BackwardsKaiserBesselKernel, BSplineKernel, Di
                    FastApproximation, GaussianKernel, HalfSupport, KaiserBesselKernel, NUFFTCallbacks, NUFFTError,
                    PlanNUFFT, exec_type1, exec_type2, launch_count, set_points)
 
+from .nfft import NFFTPlan, accuracy_params, mul, mul_adjoint, nodes, plan_nfft
 from .distributed import PointPartitionedNUFFT, TransformShardedNUFFT, partition_points, shard_transforms
 
 __all__ = [
     "PointPartitionedNUFFT", "TransformShardedNUFFT", "partition_points", "shard_transforms",
+    "NFFTPlan", "plan_nfft", "nodes", "mul", "mul_adjoint", "accuracy_params",
     "PlanNUFFT", "set_points", "exec_type1", "exec_type2", "HalfSupport", "NUFFTCallbacks",
     "KaiserBesselKernel", "BackwardsKaiserBesselKernel", "GaussianKernel", "BSplineKernel",
     "Direct", "FastApproximation", "ArgumentError", "DimensionMismatch", "NUFFTError", "launch_count",

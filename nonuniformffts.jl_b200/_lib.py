@@ -64,6 +64,7 @@ SYMBOLS = {
     "nufft_plan_shape": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "nufft_plan_kernel_info": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), _VP, _VP]),
     "nufft_set_points": (C.c_int, [_VP, C.c_int64, _PP]),
+    "nufft_set_points_matrix": (C.c_int, [_VP, C.c_int64, _VP]),
     "nufft_get_binning": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nufft_get_binning_fine": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nufft_exec_type1": (C.c_int, [_VP, _PP, _PP, C.POINTER(nufft_callbacks)]),

@@ -165,6 +165,18 @@ int nufft_set_points(nufft_plan h, int64_t np, const void *const x[])
     return binning_set_points(p, np, x);
 }
 
+int nufft_set_points_matrix(nufft_plan h, int64_t np, const void *xmat)
+{
+    NUFFT_TRY(check_plan(h));
+    Plan &p = *reinterpret_cast<Plan *>(h);
+    if (!xmat && np > 0) { set_error("null point matrix"); return NUFFT_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(p.device));
+    // column-major (D, Np) matrix == array of D-vectors: coordinate d of point i at xmat[i * D + d]; read in place by K-bin
+    const void *x[3] = {nullptr, nullptr, nullptr};
+    for (int d = 0; d < p.D; ++d) x[d] = (const char *)xmat + (size_t)d * p.real_bytes;
+    return binning_set_points(p, np, x, p.D);
+}
+
 int nufft_get_binning(nufft_plan h, const int32_t **perm, const int32_t **bin_offsets, int64_t *nbins, int64_t bin_dims[3])
 {
     NUFFT_TRY(check_plan(h));

@@ -36,6 +36,7 @@ struct BinGeom {
     int B[3];
     int nb[3];
     int convention;
+    int xstride;     // element stride of the point arrays: 1 (D separate vectors) or D (one (D, Np) matrix)
     int rt;          // sub-bin refinement active (TileGeom::rt)
     int sub[3];
     int nsub;
@@ -66,20 +67,20 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
         uint32_t key = 0xffffffffu;
         if (valid) {
             T r;
-            T f0 = fold_point<T>(x0[i], g.convention), f1 = (T)0, f2 = (T)0;
+            T f0 = fold_point<T>(x0[i * g.xstride], g.convention), f1 = (T)0, f2 = (T)0;
             int c = point_to_cell0<T>(f0, g.N[0], r);
             int b = c / g.B[0];
             uint32_t k = (uint32_t)b;
             int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // rt: 4-cell columns in x, y; single cells in z
             if (g.D > 1) {
-                f1 = fold_point<T>(x1[i], g.convention);
+                f1 = fold_point<T>(x1[i * g.xstride], g.convention);
                 c = point_to_cell0<T>(f1, g.N[1], r);
                 b = c / g.B[1];
                 sy = (c - b * g.B[1]) >> 2;
                 k += (uint32_t)b * (uint32_t)g.nb[0];
             }
             if (g.D > 2) {
-                f2 = fold_point<T>(x2[i], g.convention);
+                f2 = fold_point<T>(x2[i * g.xstride], g.convention);
                 c = point_to_cell0<T>(f2, g.N[2], r);
                 b = c / g.B[2];
                 sz = c - b * g.B[2];
@@ -312,14 +313,14 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__rest
 // ---- sorted, folded copy of the points ---------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-gather_points_kernel(int D, int convention, int64_t np, const int32_t *__restrict__ perm,
+gather_points_kernel(int D, int convention, int xstride, int64_t np, const int32_t *__restrict__ perm,
                      const T *__restrict__ x0, const typename PointRec<T>::type *__restrict__ rec,
                      T *__restrict__ y0, T *__restrict__ y1, T *__restrict__ y2)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= np) return;
     const int32_t i = perm[k];
-    if (D == 1) { y0[k] = fold_point<T>(x0[i], convention); return; }
+    if (D == 1) { y0[k] = fold_point<T>(x0[(int64_t)i * xstride], convention); return; }
     const typename PointRec<T>::type r = rec[i];          // folded in bin_keys_kernel: one sector per point
     y0[k] = r.x;
     y1[k] = r.y;
@@ -398,6 +399,7 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     BinGeom bg;
     bg.D = p.D;
     bg.convention = p.opts.point_convention;
+    bg.xstride = p.x_stride;
     for (int d = 0; d < 3; ++d) { bg.N[d] = g.N[d]; bg.B[d] = g.B[d]; bg.nb[d] = g.nb[d]; bg.sub[d] = g.sub[d]; }
     bg.rt = g.rt;
     bg.nsub = g.nsub;
@@ -479,7 +481,7 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
     }
     if (np > 0) {
         gather_points_kernel<T><<<(unsigned)cdiv(np, 256), 256, 0, st>>>(
-            p.D, p.opts.point_convention, np, p.d_perm, (const T *)x[0], (const typename PointRec<T>::type *)p.d_rec,
+            p.D, p.opts.point_convention, p.x_stride, np, p.d_perm, (const T *)x[0], (const typename PointRec<T>::type *)p.d_rec,
             (T *)p.d_xs[0], (T *)p.d_xs[1], (T *)p.d_xs[2]);
         NUFFT_COUNT_LAUNCH();
     }
@@ -525,8 +527,9 @@ int binning_coarse_perm(Plan &p, const int32_t **perm)
     return NUFFT_SUCCESS;
 }
 
-int binning_set_points(Plan &p, int64_t np, const void *const x[])
+int binning_set_points(Plan &p, int64_t np, const void *const x[], int xstride)
 {
+    p.x_stride = xstride;
     if (np < 0) { set_error("negative number of points"); return NUFFT_ERR_ARG; }
     if (np >= ((int64_t)1 << 31) - 4096) { set_error("number of points exceeds maximum allowed: 2^31"); return NUFFT_ERR_ARG; }
     for (int d = 0; d < p.D; ++d) {

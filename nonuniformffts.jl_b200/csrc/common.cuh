@@ -177,6 +177,7 @@ struct Plan {
     int64_t Np = -1;
     int64_t cap = 0;                 // capacity (points) of the buffers below
     const void *user_x[3] = {nullptr, nullptr, nullptr};
+    int x_stride = 1;                // element stride of the user's point arrays (D for a (D, Np) matrix)
     uint32_t *d_keys[2] = {nullptr, nullptr};
     int32_t *d_vals[2] = {nullptr, nullptr};
     int32_t *d_perm = nullptr;       // alias into d_vals
@@ -223,7 +224,7 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ---- stage implementations (one .cu each) ---------------------------------------------------
 int host_plan_init(Plan &p);                 // host_plan.cu: sizes, kernel data, tables, geometry, FFT plans
 void host_plan_free(Plan &p);
-int binning_set_points(Plan &p, int64_t np, const void *const x[]);        // binning.cu
+int binning_set_points(Plan &p, int64_t np, const void *const x[], int xstride = 1);        // binning.cu
 int spread_run(Plan &p, const void *const vp[], const nufft_callbacks *cb); // spread_*.cu
 int interp_run(Plan &p, void *const vp[], const nufft_callbacks *cb);       // interp_*.cu
 int deconv_type1_run(Plan &p, void *const uhat[], const nufft_callbacks *cb); // deconv.cu

@@ -46,16 +46,16 @@ template <typename T> struct PfftArgs {
 template <typename T> __host__ __device__ constexpr int pf_group() { return 128 / (2 * (int)sizeof(T)); }
 template <typename T> __host__ __device__ constexpr int pf_tw(int L)
 {
-    const int maxel = 65536 / (2 * (int)sizeof(T));       // <= 64 KiB of line data per CTA
+    const int maxel = 32768 / (2 * (int)sizeof(T));       // <= 32 KiB of line data per CTA: 4 CTAs per SM overlap their phases
     return pf_group<T>() < maxel / L ? pf_group<T>() : (maxel / L > 0 ? maxel / L : 1);
 }
 template <typename T> __host__ __device__ constexpr int pf_nt(int L)
 {
-    return pf_tw<T>(L) * L / 8 < 512 ? pf_tw<T>(L) * L / 8 : 512;
+    return pf_tw<T>(L) * L / 8 < 256 ? pf_tw<T>(L) * L / 8 : 256;
 }
 template <typename T> __host__ __device__ constexpr size_t pf_smem(int L)
 {
-    return (size_t)(pf_tw<T>(L) * (L + 1) + L) * 2 * sizeof(T);
+    return (size_t)(pf_tw<T>(L) * L + 2 * L) * 2 * sizeof(T);       // tile (no padding: lines are XOR-swizzled) + twiddles
 }
 
 template <typename C2> __device__ __forceinline__ C2 c_add(C2 a, C2 b) { C2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
@@ -68,6 +68,48 @@ template <typename C2> __device__ __forceinline__ C2 c_mul(C2 a, C2 b)
     return r;
 }
 template <typename C2> __device__ __forceinline__ C2 c_mul_mi(C2 a) { C2 r; r.x = a.y; r.y = -a.x; return r; }   // a * (-i)
+
+// Float32: packed 2 x f32 instructions of sm_100a (FADD2 / FMUL2 / FFMA2) — one instruction per complex add, two per
+// complex multiplication by a twiddle stored as (c, s, -s, c)
+__device__ __forceinline__ unsigned long long pf_pk(float2 a)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 pf_unpk(unsigned long long v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+template <> __device__ __forceinline__ float2 c_add<float2>(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pf_pk(a)), "l"(pf_pk(b)));
+    return pf_unpk(d);
+}
+template <> __device__ __forceinline__ float2 c_sub<float2>(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pf_pk(a)), "l"(pf_pk(b)));
+    return pf_unpk(d);
+}
+// a * w with w given as wa = (c, s), wb = (-s, c):  (a.x c - a.y s, a.x s + a.y c) = a.x * wa + a.y * wb
+__device__ __forceinline__ float2 c_mul_tw(float2 a, float2 wa, float2 wb)
+{
+    unsigned long long t, d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pf_pk(make_float2(a.y, a.y))), "l"(pf_pk(wb)));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pf_pk(make_float2(a.x, a.x))), "l"(pf_pk(wa)), "l"(t));
+    return pf_unpk(d);
+}
+__device__ __forceinline__ double2 c_mul_tw(double2 a, double2 wa, double2 wb)
+{
+    double2 r;
+    r.x = a.x * wa.x + a.y * wb.x;
+    r.y = a.x * wa.y + a.y * wb.y;
+    return r;
+}
 
 // forward DFT of R points in registers (R = 2, 4, 8), natural output order
 template <typename T, int R> __device__ __forceinline__ void dft(typename Vec2<T>::type (&u)[R])
@@ -114,12 +156,20 @@ template <typename T> __host__ __device__ constexpr int pf_phys(int i)
     constexpr int G = pf_group<T>();
     return i ^ ((i / G) & (G - 1));
 }
+// element (line, i) of the tile: lines are L apart (a power of two, no padding) and additionally rotated by the line
+// index inside each 128-byte group, so that the same position of 16 different lines (strided global passes) hits 16
+// different banks.  line * L + (phys(i) ^ (line % G)): the XOR constants of the butterflies stay below L.
+template <typename T, int L> __device__ __forceinline__ int pf_slot(int line, int physpos)
+{
+    constexpr int G = pf_group<T>();
+    return line * L + (physpos ^ (line & (G - 1) & (L - 1)));
+}
 
 // one in-place Stockham pass of radix R with Ns = P already transformed
 template <typename T, int L, int P, int R> __device__ __forceinline__ void pf_pass(typename Vec2<T>::type *s, const typename Vec2<T>::type *tw, int tid)
 {
     using C2 = typename Vec2<T>::type;
-    constexpr int TW = pf_tw<T>(L), NT = pf_nt<T>(L), LS = L + 1;
+    constexpr int TW = pf_tw<T>(L), NT = pf_nt<T>(L);
     constexpr int TL = L / R;                       // butterflies per line
     constexpr int NB = TW * TL / NT;                // butterflies per thread
     static_assert(NB >= 1 && NB * NT == TW * TL, "pfft thread mapping");
@@ -134,14 +184,16 @@ template <typename T, int L, int P, int R> __device__ __forceinline__ void pf_pa
 #pragma unroll
     for (int bi = 0; bi < NB; ++bi) {
         const int j = jj[bi], k = j & (P - 1);
-        const C2 *sl = s + line[bi] * LS;
-        const int pj = pf_phys<T>(j);
+        const int pa = pf_slot<T, L>(line[bi], pf_phys<T>(j));     // j and t TL occupy disjoint bits below L
 #pragma unroll
-        for (int t = 0; t < R; ++t) u[bi][t] = sl[pj ^ pf_phys<T>(t * TL)];
+        for (int t = 0; t < R; ++t) u[bi][t] = s[pa ^ pf_phys<T>(t * TL)];
         if constexpr (P > 1) {
             constexpr int OFF = pf_tw_offset(L, P);
 #pragma unroll
-            for (int t = 1; t < R; ++t) u[bi][t] = c_mul(u[bi][t], tw[OFF + (t - 1) * P + k]);
+            for (int t = 1; t < R; ++t) {
+                const C2 *w2 = tw + 2 * (OFF + (t - 1) * P + k);        // (c, s), (-s, c): one 16-byte (Float32) load
+                u[bi][t] = c_mul_tw(u[bi][t], w2[0], w2[1]);
+            }
         }
         dft<T, R>(u[bi]);
     }
@@ -149,10 +201,9 @@ template <typename T, int L, int P, int R> __device__ __forceinline__ void pf_pa
 #pragma unroll
     for (int bi = 0; bi < NB; ++bi) {
         const int j = jj[bi], k = j & (P - 1);
-        const int pb = pf_phys<T>((j - k) * R + k);          // (j - k) R, t P and k occupy disjoint bits
-        C2 *sl = s + line[bi] * LS;
+        const int pb = pf_slot<T, L>(line[bi], pf_phys<T>((j - k) * R + k));   // (j - k) R, t P and k occupy disjoint bits
 #pragma unroll
-        for (int t = 0; t < R; ++t) sl[pb ^ pf_phys<T>(t * P)] = u[bi][t];
+        for (int t = 0; t < R; ++t) s[pb ^ pf_phys<T>(t * P)] = u[bi][t];
     }
     __syncthreads();
 }
@@ -194,15 +245,15 @@ __device__ __noinline__ T pf_callback_factor(const T *fdense, const T *f0, const
 // (the tile is TW consecutive lines = one contiguous block of memory); otherwise TW consecutive elements of the
 // contiguous dimension times a strided line.
 template <typename T, int L, bool FWD, bool CONTIG>
-__global__ void __launch_bounds__(pf_nt<T>(L), pf_nt<T>(L) >= 512 ? 2 : 3) pfft_pass_kernel(PfftArgs<T> a)
+__global__ void __launch_bounds__(pf_nt<T>(L), 4) pfft_pass_kernel(PfftArgs<T> a)
 {
     using C2 = typename Vec2<T>::type;
-    constexpr int TW = pf_tw<T>(L), NT = pf_nt<T>(L), LS = L + 1;
+    constexpr int TW = pf_tw<T>(L), NT = pf_nt<T>(L);
     constexpr int EPT = TW * L / NT;                // elements per thread
     static_assert(NT % TW == 0 && (NT % L == 0 || L % NT == 0), "pfft thread mapping");
     extern __shared__ __align__(16) unsigned char pf_raw[];
-    C2 *s = reinterpret_cast<C2 *>(pf_raw);         // [TW][LS]
-    C2 *tw = s + TW * LS;                           // concatenated per-pass twiddle tables (< L entries)
+    C2 *s = reinterpret_cast<C2 *>(pf_raw);         // [TW][L], swizzled (pf_slot)
+    C2 *tw = s + TW * L;                            // concatenated per-pass twiddle tables, two entries per twiddle
     const int tid = threadIdx.x;
     const int K = a.K;
     int64_t lo0 = 0, hi0 = 0;
@@ -216,7 +267,7 @@ __global__ void __launch_bounds__(pf_nt<T>(L), pf_nt<T>(L) >= 512 ? 2 : 3) pfft_
         lo0 = (int64_t)(blockIdx.x % tiles_lo) * TW;
         nlines = (int)(a.n_lo - lo0 < TW ? a.n_lo - lo0 : TW);
     }
-    for (int i = tid; i < pf_tw_offset(L, L); i += NT) tw[i] = a.tw[i];
+    for (int i = tid; i < 2 * pf_tw_offset(L, L); i += NT) tw[i] = a.tw[i];
 
     // deconvolution factor (and uniform callback, on the user's side only) of kept index I of line `line`
     const bool has_cb = a.user_side && (a.fdense || a.fsep[0] || a.fsep[1] || a.fsep[2]);
@@ -257,10 +308,10 @@ __global__ void __launch_bounds__(pf_nt<T>(L), pf_nt<T>(L) >= 512 ? 2 : 3) pfft_
             }
         }
 #pragma unroll
-        for (int n = 0; n < EPT; ++n) s[full_line(n) * LS + full_pos(n)] = r[n];
+        for (int n = 0; n < EPT; ++n) s[pf_slot<T, L>(full_line(n), full_pos(n))] = r[n];
     } else {
         C2 z; z.x = 0; z.y = 0;
-        for (int e = tid; e < TW * LS; e += NT) s[e] = z;
+        for (int e = tid; e < TW * L; e += NT) s[e] = z;
         C2 r[EPT];
         int pos[EPT];
         int line = CONTIG ? tid / K : tid % TW, I = CONTIG ? tid % K : tid / TW;
@@ -271,7 +322,7 @@ __global__ void __launch_bounds__(pf_nt<T>(L), pf_nt<T>(L) >= 512 ? 2 : 3) pfft_
                 const C2 v = a.in[kept_base + n * full_step];
                 const T f = factor(line, I);
                 r[n].x = v.x * f; r[n].y = -(v.y * f);
-                pos[n] = line * LS + pf_phys<T>(a.imap[I]);
+                pos[n] = pf_slot<T, L>(line, pf_phys<T>(a.imap[I]));
             }
             if constexpr (CONTIG) { I += NT; while (I >= K) { I -= K; ++line; } }
             else I += NT / TW;
@@ -286,15 +337,19 @@ __global__ void __launch_bounds__(pf_nt<T>(L), pf_nt<T>(L) >= 512 ? 2 : 3) pfft_
 
     // ---- store --------------------------------------------------------------------------------------------------
     if constexpr (FWD) {
+        // rolled loop: K <= L kept modes per line, so up to half of the EPT slots of a thread are empty
         int line = CONTIG ? tid / K : tid % TW, I = CONTIG ? tid % K : tid / TW;
-#pragma unroll
+        C2 *dst = a.out + kept_base;
+#pragma unroll 4
         for (int n = 0; n < EPT; ++n) {
-            if (line < nlines && I < K) {
-                C2 v = s[line * LS + pf_phys<T>(a.imap[I])];
+            if (CONTIG ? line >= nlines : I >= K) break;
+            if (CONTIG || line < nlines) {
+                C2 v = s[pf_slot<T, L>(line, pf_phys<T>(a.imap[I]))];
                 const T f = factor(line, I);
                 v.x *= f; v.y *= f;
-                a.out[kept_base + n * full_step] = v;
+                *dst = v;
             }
+            dst += full_step;
             if constexpr (CONTIG) { I += NT; while (I >= K) { I -= K; ++line; } }
             else I += NT / TW;
         }
@@ -302,7 +357,7 @@ __global__ void __launch_bounds__(pf_nt<T>(L), pf_nt<T>(L) >= 512 ? 2 : 3) pfft_
         if (nlines == TW) {
 #pragma unroll
             for (int n = 0; n < EPT; ++n) {
-                C2 v = s[full_line(n) * LS + full_pos(n)];
+                C2 v = s[pf_slot<T, L>(full_line(n), full_pos(n))];
                 v.y = -v.y;
                 a.out[full_base + n * full_step] = v;
             }
@@ -310,7 +365,7 @@ __global__ void __launch_bounds__(pf_nt<T>(L), pf_nt<T>(L) >= 512 ? 2 : 3) pfft_
 #pragma unroll
             for (int n = 0; n < EPT; ++n) {
                 if (full_line(n) < nlines) {
-                    C2 v = s[full_line(n) * LS + full_pos(n)];
+                    C2 v = s[pf_slot<T, L>(full_line(n), full_pos(n))];
                     v.y = -v.y;
                     a.out[full_base + n * full_step] = v;
                 }
@@ -376,7 +431,7 @@ template <typename T> static int pfft_init_t(Plan &p)
     using C2 = typename Vec2<T>::type;
     for (int d = 0; d < p.D; ++d) {
         const int L = (int)p.Nos[d];
-        std::vector<C2> h((size_t)L);
+        std::vector<C2> h((size_t)2 * L);               // two entries per twiddle: (c, s), (-s, c)
         for (int P = 1; P < L; P *= pf_radix(L, P)) {
             const int R = pf_radix(L, P);
             if (P == 1) continue;
@@ -384,8 +439,11 @@ template <typename T> static int pfft_init_t(Plan &p)
             for (int t = 1; t < R; ++t)
                 for (int k = 0; k < P; ++k) {
                     const double ang = -2.0 * M_PI * (double)t * (double)k / ((double)P * (double)R);
-                    h[(size_t)off + (size_t)(t - 1) * P + k].x = (T)std::cos(ang);
-                    h[(size_t)off + (size_t)(t - 1) * P + k].y = (T)std::sin(ang);
+                    const size_t e = 2 * ((size_t)off + (size_t)(t - 1) * P + k);
+                    h[e].x = (T)std::cos(ang);
+                    h[e].y = (T)std::sin(ang);
+                    h[e + 1].x = -h[e].y;
+                    h[e + 1].y = h[e].x;
                 }
         }
         {   // 1 / phihat_d in precision T
@@ -395,8 +453,8 @@ template <typename T> static int pfft_init_t(Plan &p)
             CUDA_TRY(cudaMalloc(&p.d_pf_iph[d], inv.size() * sizeof(T)));
             CUDA_TRY(cudaMemcpy(p.d_pf_iph[d], inv.data(), inv.size() * sizeof(T), cudaMemcpyHostToDevice));
         }
-        CUDA_TRY(cudaMalloc(&p.d_pf_tw[d], (size_t)L * sizeof(C2)));
-        CUDA_TRY(cudaMemcpy(p.d_pf_tw[d], h.data(), (size_t)L * sizeof(C2), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc(&p.d_pf_tw[d], h.size() * sizeof(C2)));
+        CUDA_TRY(cudaMemcpy(p.d_pf_tw[d], h.data(), h.size() * sizeof(C2), cudaMemcpyHostToDevice));
     }
     // scratch A: [K0][N1][N2] (3-D) or [K0][N1] (2-D); the second 3-D intermediate [K0][K1][N2] lives in the grid itself
     size_t na = 0;

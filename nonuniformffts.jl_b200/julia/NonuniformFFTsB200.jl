@@ -145,6 +145,17 @@ function set_points!(p::B200Plan{Z, N}, xp::NTuple{N, Any}) where {Z, N}
 end
 set_points!(p::B200Plan{Z, 1}, xp::AbstractVector{<:Real}) where {Z} = set_points!(p, (xp,))
 
+"""    set_points!(p, xp::AbstractMatrix)   — src/set_points.jl:76-88 (size(xp) == (N, Np)); also serves a
+`Vector{SVector{N}}` through `reinterpret(reshape, T, xp)` (src/set_points.jl:62-74).  The reference copies the
+matrix into N vectors; here the array-of-points layout is read in place by the binning kernel."""
+function set_points!(p::B200Plan{Z, N}, xp::AbstractMatrix{<:Real}) where {Z, N}
+    size(xp, 1) == N || throw(DimensionMismatch(lazy"expected input matrix to have dimensions ($N, Np)"))
+    eltype(xp) === real(Z) || throw(ArgumentError("input points must have the same accuracy as the created plan"))
+    ccall((:nufft_set_points_matrix, libnufft), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), p.handle, size(xp, 2), devptr(xp)) |> check
+    p.points = xp
+    p
+end
+
 function _callbacks(cb)
     cb === nothing && return C_NULL
     # cb = (nonuniform = weights::DeviceVector | nothing, uniform = factor::DeviceArray | nothing)

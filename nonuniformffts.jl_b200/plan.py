@@ -297,7 +297,8 @@ class PlanNUFFT:
     # -- set_points! ----------------------------------------------------------------------------
     def set_points(self, xp) -> "PlanNUFFT":
         """set_points!(p, xp): tuple of D vectors (preferred), a single vector in 1-D, or a (Np, D)
-        tensor == Julia (d, Np) matrix (copied to SoA, as src/set_points.jl:76-88 does)."""
+        tensor == Julia (d, Np) matrix / Vector{SVector{D}} (src/set_points.jl:62-88; read in place by the
+        binning kernel through nufft_set_points_matrix when contiguous)."""
         D = self._ndims
         if isinstance(xp, torch.Tensor):
             if xp.ndim == 1:
@@ -307,6 +308,17 @@ class PlanNUFFT:
             elif xp.ndim == 2:
                 if xp.shape[1] != D:
                     raise DimensionMismatch(f"expected input matrix to have dimensions ({D}, Np)")
+                if xp.is_contiguous():
+                    if xp.dtype != self.real_dtype:
+                        raise ArgumentError(
+                            f"input points must have the same accuracy as the created plan (got {xp.dtype} points for a {self.dtype} plan)")
+                    self._check_dev(xp, "points")
+                    self.points = (xp,)
+                    self.Np = xp.shape[0]
+                    _check(self._lib.nufft_set_points_matrix(self._h, self.Np, C.c_void_p(xp.data_ptr())))
+                    if self.synchronise:
+                        self.stream.synchronize()
+                    return self
                 xp = tuple(xp[:, d].contiguous() for d in range(D))
             else:
                 raise ArgumentError("unexpected point container")

@@ -54,3 +54,12 @@ def test_no_cpu_fallback_in_product_package():
     for f in pkg.glob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_nfft_accuracy_params():
+    """AbstractNFFTs.accuracyParams restated in the host mirror (no GPU needed)."""
+    import nufft_b200 as nb
+    assert nb.accuracy_params() == (4, 2.0, 1e-7)
+    m, sigma, reltol = nb.accuracy_params(reltol=1e-9)
+    assert (m, sigma) == (5, 2.0) and reltol == 1e-9
+    assert nb.accuracy_params(m=6, sigma=1.5)[:2] == (6, 1.5)

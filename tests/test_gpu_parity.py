@@ -223,3 +223,66 @@ def test_pruned_fft_vs_cufft(nufft, monkeypatch):
         outs.append((u.cpu().numpy(), v.cpu().numpy()))
         gp.close()
     assert l2_error(outs[0][0], outs[1][0]) <= 2e-6 and l2_error(outs[0][1], outs[1][1]) <= 2e-6
+
+
+def test_matrix_points_read_in_place(nufft, oracle_mod):
+    """set_points!(p, xp::Matrix (D, Np)) / Vector{SVector{D}} (src/set_points.jl:62-88): the array-of-points layout is
+    read in place by K-bin (nufft_set_points_matrix); binning and results equal the tuple-of-vectors path exactly."""
+    import torch
+    rng = np.random.default_rng(50)
+    for dtype, dims in ((np.complex64, (24, 20, 16)), (np.float64, (30, 18)), (np.complex128, (64,))):
+        rt = real_of(dtype)
+        Np, D = 5000, len(dims)
+        xs = make_points(rng, D, Np, rt, "uniform")
+        vp = to_dev(make_values(rng, Np, dtype))
+        mat = to_dev(np.ascontiguousarray(np.stack(xs, axis=1)))            # (Np, D) row-major == Julia (D, Np)
+        outs, perms = [], []
+        for pts in (tuple(to_dev(x) for x in xs), mat):
+            gp = gpu_plan(nufft, dtype, dims, m=4, sigma=2.0)
+            gp.set_points(pts)
+            perm, off, _ = gp.binning()
+            u = torch.empty(gp.shape, dtype=torch.complex64 if rt == np.float32 else torch.complex128, device="cuda")
+            gp.exec_type1(u, vp)
+            v = torch.empty_like(vp)
+            gp.exec_type2(v, u)
+            outs.append((u.cpu().numpy(), v.cpu().numpy()))
+            perms.append((perm.cpu().numpy().copy(), off.cpu().numpy().copy()))
+            gp.close()
+        assert np.array_equal(perms[0][0], perms[1][0]) and np.array_equal(perms[0][1], perms[1][1])
+        # same kernels, same order of operations except for the atomic flush order of the tiles
+        assert l2_error(outs[1][0], outs[0][0]) <= 10 * np.finfo(rt).eps and l2_error(outs[1][1], outs[0][1]) <= 10 * np.finfo(rt).eps
+
+
+@pytest.mark.parametrize("rt", [np.float32, np.float64])
+def test_nfft_frontend_vs_ndft(nufft, rt):
+    """AbstractNFFTs front-end (src/abstractNFFTs.jl:115-245; test/abstractNFFTs.jl compares with NFFT.jl): nodes in
+    [-1/2, 1/2), mul! = sum_k fhat_k exp(-2 pi i k x_j), adjoint = sum_j f_j exp(+2 pi i k x_j), k = -N/2 .. N/2 - 1
+    in increasing order.  Checked against the direct sums."""
+    import torch
+    rng = np.random.default_rng(51)
+    ct = complex_of(rt)
+    for Ns in ((32,), (16, 12), (8, 10, 12)):
+        D, Np = len(Ns), 300
+        x = (rng.random((Np, D)) - 0.5).astype(rt)
+        fhat = (rng.standard_normal(Ns[::-1]) + 1j * rng.standard_normal(Ns[::-1])).astype(ct)   # torch (C-order) shape
+        f = (rng.standard_normal(Np) + 1j * rng.standard_normal(Np)).astype(ct)
+        p = nufft.plan_nfft(to_dev(x), Ns, m=4, sigma=2.0)          # HalfSupport(4), sigma = 2: ~1e-7 (src/plan.jl:187-194)
+        assert p.size_in() == tuple(Ns) and p.size_out() == (Np,)
+        ks = [np.arange(-(n // 2), (n + 1) // 2) for n in Ns]
+        # phase[j, k_D.., k_1] (C order: last axis = first Julia dimension)
+        ph = np.zeros((Np,) + tuple(Ns[::-1]))
+        for d in range(D):
+            shape = [1] * (D + 1)
+            shape[D - d] = Ns[d]
+            ph = ph + x[:, d].astype(np.float64).reshape((Np,) + (1,) * D) * ks[d].reshape(shape)
+        E = np.exp(-2j * np.pi * ph)
+        ref_fwd = (E * fhat.astype(np.complex128)[None]).reshape(Np, -1).sum(axis=1)
+        ref_adj = (np.conj(E) * f.astype(np.complex128).reshape((Np,) + (1,) * D)).sum(axis=0)
+        out = torch.empty(Np, dtype=torch.complex64 if rt == np.float32 else torch.complex128, device="cuda")
+        nufft.mul(out, p, to_dev(fhat))
+        adj = torch.empty(Ns[::-1], dtype=out.dtype, device="cuda")
+        nufft.mul_adjoint(adj, p, to_dev(f))
+        tol = 2e-5 if rt == np.float32 else 1e-6
+        assert l2_error(out.cpu().numpy(), ref_fwd) <= tol, l2_error(out.cpu().numpy(), ref_fwd)
+        assert l2_error(adj.cpu().numpy(), ref_adj) <= tol, l2_error(adj.cpu().numpy(), ref_adj)
+        p.close()
