@@ -84,6 +84,7 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
                 c = point_to_cell0<T>(f2, g.N[2], r);
                 b = c / g.B[2];
                 sz = c - b * g.B[2];
+                if (g.rt >= 2) sz >>= 2;                       // wp / cs: sub-bins (layers) of 4 cells in z
                 k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
             }
             // rt plans: refine by (column, z cell) so that the points of a 4x4-cell column are contiguous and

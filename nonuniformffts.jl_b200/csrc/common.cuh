@@ -124,7 +124,8 @@ struct TileGeom {
     int batch;       // points per evaluation batch (shared-memory staging)
     // register-window fast path (rt_spread.cuh / rt_interp.cuh; D = 3, M = 4, Float32): bins are refined into
     // columns of 4 x 4 cells and single cells along z; the sort key is bin * nsub + ((cy * sub[0] + cx) * sub[2] + cz)
-    int rt;          // 1 when the fast path is active
+    int rt;          // 1: register-window kernels (rt_*.cuh); 2: warp-private-tile kernels (wp_*.cuh: bins 8^3, sub-bins 4^3);
+                     // 3: column-streaming kernels (cs_*.cuh: bins 4 x 4 x 64, layers of 4 cells)
     int sub[3];      // sub-bins per bin along each dimension (1 when !rt)
     int nsub;        // sub[0] * sub[1] * sub[2]
 };
@@ -215,6 +216,10 @@ static inline int record_size(int D, int M)
 }
 
 // floats per point record of the register-tile kernels (rt_common.cuh)
+// warp-private-tile kernels are the default for their configuration class (NUFFT_B200_WP=0 disables)
+#ifndef NUFFT_WP_DEFAULT
+#define NUFFT_WP_DEFAULT 0
+#endif
 constexpr int RT_REC_F = 52;
 constexpr int RT_SREC_F = 60;      // spreading records carry value x wz (complex): rt_spread.cuh
 

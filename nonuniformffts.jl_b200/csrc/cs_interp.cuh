@@ -1,0 +1,242 @@
+// cs_interp.cuh — K-interp, column-streaming variant (3-D, HalfSupport(4), ComplexF32).  Mirror image of cs_spread.cuh;
+// replaces src/interpolation/gpu.jl:211-395 for this configuration class (same sums, different order).
+//
+// A warp walks through a chunk of the points ordered by (z segment, column of 4 x 4 cells, layer of 4 cells) and keeps
+// the padded footprint of the current layer (11 x 11 x 11 grid values) in registers, lane L holding the columns
+// rt::lane_slots(L):
+//   per point   8 shared-memory loads of the point's record (zero-padded 1-D weights), 44 FFMA2 (t_k = sum_i G[k][i] wz[i])
+//               + 2 FMUL2 + 4 FFMA2 (sum_k t_k wx wy) per lane; the lane partial goes to a warp-private shared-memory
+//               row (one STS.64) — no dependent shuffle chain in the loop;
+//   per batch   3 lanes per point add up the 32 partials of that point (11 LDS.64 each, rows padded to 35 -> no bank
+//               conflicts) + 2 shuffles; prefactor, non-uniform callback, scatter through the permutation;
+//   next layer  7 planes move down in the register file; the 4 new planes were requested from global memory (L2) when
+//               the window arrived at the CURRENT layer (16 loads per lane into spare registers), so their latency is
+//               covered by the ~8 points of the layer;
+//   new column  44 loads per lane (rows of 11 consecutive cells).
+#pragma once
+#include "cs_spread.cuh"
+
+namespace nufft {
+namespace cs {
+
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m)
+{
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m);
+    const unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_down_u64(u64 v, int d)
+{
+    const unsigned lo = __shfl_down_sync(0xffffffffu, (unsigned)v, d);
+    const unsigned hi = __shfl_down_sync(0xffffffffu, (unsigned)(v >> 32), d);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ u64 shfl_idx_u64(u64 v, int src)
+{
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src);
+    const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+constexpr int PART_LD = 35;               // row length of the lane-partial buffer (u64): 35 = 3 mod 16 -> lane 3p + d reads bank pair (lane + 3j) mod 16
+
+__device__ __forceinline__ u64 ldg_cell(const float2 *p)
+{
+    u64 v;
+    asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
+__global__ void __launch_bounds__(32 * NWARP)
+cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__restrict__ perm, int32_t *work_counter,
+                 const float *__restrict__ xs0, const float *__restrict__ xs1, const float *__restrict__ xs2, MutPtrPack vp, int C,
+                 const float2 *__restrict__ us, int64_t ncells, float prefactor, const float *__restrict__ nu_weights)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH][REC_F]
+    u64 *part_all = (u64 *)(rec_all + NWARP * BATCH * REC_F);                // [NWARP][BATCH][PART_LD] lane partials
+    float *cs_s = (float *)(part_all + NWARP * BATCH * PART_LD);             // [3][cs_stride]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    float *rec_w = rec_all + warp * BATCH * REC_F;
+    u64 *part_w = part_all + warp * BATCH * PART_LD;
+
+    for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
+    __syncthreads();                                   // the only CTA barrier: coefficient tables
+
+    const rt::LaneSlots ls = rt::lane_slots(lane);
+    const int ep = lane / 3, ed = lane - 3 * ep;       // evaluation role: lane = 3 * point + dimension
+    const bool elane = lane < 3 * BATCH;
+    const float *xs_d = ed == 0 ? xs0 : (ed == 1 ? xs1 : xs2);
+    const KernelParams<float> kl = lane_kernel_params(kp, ed);
+    const float *cs_d = cs_s + ed * kp.cs_stride;
+    const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
+    const int plane = Nx * Ny;
+
+    u64 G[4][P];                                       // window: planes COL * wl - 3 .. COL * wl + 7
+    u64 H[4][COL];                                     // the 4 planes above it, requested ahead
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) G[k][i] = 0ull;
+#pragma unroll
+        for (int i = 0; i < COL; ++i) H[k][i] = 0ull;
+    }
+
+    while (true) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1);
+        item = __shfl_sync(FULL, item, 0);
+        const int64_t k0l = (int64_t)item * CHUNK;
+        if (k0l >= np) break;
+        const int k0 = (int)k0l, k1 = min(k0 + CHUNK, np);
+        const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
+
+        for (int c = 0; c < C; ++c) {
+            float2 *vc = (float2 *)vp.p[c];
+            const float2 *u = us + (int64_t)c * ncells;
+            int wcol = -1, wl = 0;                         // column id (cy << 16 | cx), layer
+            int goff[4] = {0, 0, 0, 0};                    // cell offsets of the lane's 4 columns inside a z plane
+
+            auto request_ahead = [&]() {                   // planes P .. P + 3 relative to the window (next layer's new planes)
+#pragma unroll
+                for (int i = 0; i < COL; ++i) {
+                    const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + P + i, Nz) * plane;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) H[k][i] = ldg_cell(pl + goff[k]);
+                }
+            };
+            auto load_all = [&]() {
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + i, Nz) * plane;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) G[k][i] = ldg_cell(pl + goff[k]);
+                }
+                request_ahead();
+            };
+            auto shift_one = [&]() {                       // next layer: 7 planes slide down, the requested 4 come in
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int i = 0; i < P - COL; ++i) G[k][i] = G[k][i + COL];
+#pragma unroll
+                    for (int i = 0; i < COL; ++i) G[k][P - COL + i] = H[k][i];
+                }
+                ++wl;
+                request_ahead();
+            };
+
+            float xq = 0.f;
+            auto load_x = [&](int bi) -> float {
+                const int k = k0 + bi * BATCH + ep;
+                return (elane && k < k1) ? xs_d[k] : 0.f;
+            };
+            xq = load_x(0);
+
+            for (int bi = 0; bi < nbatches; ++bi) {
+                const int kb = k0 + bi * BATCH;
+                const int nb = min(BATCH, k1 - kb);
+                const float x = xq;
+                xq = load_x(bi + 1);
+                // original index (and callback weight) of the point this lane will store (lanes 0 .. nb - 1)
+                int32_t n_out = 0;
+                if (lane < nb) n_out = perm[kb + lane];
+
+                // ---- evaluate: 3 lanes per point -----------------------------------------------------------------
+                const bool act = elane && ep < nb;
+                int cell = 0;
+                if (act) {
+                    float *r = rec_w + ep * REC_F;
+                    float w[W], pw[P];
+                    cell = eval_m4(kl, cs_d, x, w);
+                    rt::pad_shift(w, cell & 3, pw);
+                    if (ed == 1) {
+                        rt::store_y(r, pw);
+                    } else {
+                        float4 *q = reinterpret_cast<float4 *>(r + (ed == 0 ? OFF_WX : OFF_WZ));
+                        q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                        q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+                        q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
+                    }
+                }
+                int mycol, mylay;                          // lane p < nb: column id and layer of point p of the batch
+                {
+                    const int src = min(3 * ep, 27);
+                    const int c0 = __shfl_sync(FULL, cell, src), c1 = __shfl_sync(FULL, cell, src + 1);
+                    const int col = ((c1 >> 2) << 16) | (c0 >> 2);
+                    const int from = min(3 * lane + 2, 31);
+                    mycol = __shfl_sync(FULL, col, from);
+                    mylay = __shfl_sync(FULL, cell >> 2, from);
+                }
+                __syncwarp();
+
+                for (int p = 0; p < nb; ++p) {
+                    const int col = __shfl_sync(FULL, mycol, p), lay = __shfl_sync(FULL, mylay, p);
+                    if (col != wcol || lay != wl) {        // move the window (cold path)
+                        const int d = lay - wl;
+                        if (col == wcol && d == 1) {
+                            shift_one();
+                        } else {
+                            wcol = col;
+                            wl = lay;
+                            const int cx = col & 0xffff, cy = col >> 16;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                                goff[k] = wrap1(COL * cy - (M - 1) + ls.g + 3 * k, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                            goff[3] = wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx);
+                            load_all();
+                        }
+                    }
+                    const float *r = rec_w + p * REC_F;
+                    const float4 wy = *reinterpret_cast<const float4 *>(r + OFF_WY + 4 * ls.row);
+                    const float wx = r[OFF_WX + ls.x], wx3 = r[OFF_WX + ls.x3];
+                    const float4 *zq = reinterpret_cast<const float4 *>(r + OFF_WZ);
+                    const float4 z0 = zq[0], z1 = zq[1], z2 = zq[2];
+                    const float wz[P] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w, z2.x, z2.y, z2.z};
+                    u64 tk[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        const u64 wzz = pk2(wz[i], wz[i]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][i], wzz, tk[k]);
+                    }
+                    const u64 w01 = fmul2(pk2(wx, wx), pk2(wy.x, wy.y));
+                    const u64 w23 = fmul2(pk2(wx, wx3), pk2(wy.z, wy.w));
+                    const float2 wa = unpk2(w01), wb = unpk2(w23);
+                    u64 acc = fmul2(tk[0], pk2(wa.x, wa.x));
+                    acc = ffma2(tk[1], pk2(wa.y, wa.y), acc);
+                    acc = ffma2(tk[2], pk2(wb.x, wb.x), acc);
+                    acc = ffma2(tk[3], pk2(wb.y, wb.y), acc);
+                    part_w[p * PART_LD + lane] = acc;
+                }
+                __syncwarp();
+                // ---- per batch: lanes 3p, 3p + 1, 3p + 2 add up the 32 lane partials of point p -------------------------
+                u64 sum = 0ull;
+                if (act) {
+                    const u64 *row = part_w + ep * PART_LD + ed;
+#pragma unroll
+                    for (int j = 0; j < 11; ++j)
+                        if (ed + 3 * j < 32) sum = rt::fadd2(sum, row[3 * j]);
+                }
+                sum = rt::fadd2(sum, rt::fadd2(shfl_down_u64(sum, 1), shfl_down_u64(sum, 2)));   // valid in lanes 3p
+                const u64 res = shfl_idx_u64(sum, min(3 * lane, 31));                               // lane p <- lane 3p
+                if (lane < nb) {
+                    const float2 rv = unpk2(res);
+                    const float scale = prefactor * (nu_weights ? nu_weights[n_out] : 1.f);
+                    vc[n_out] = make_float2(rv.x * scale, rv.y * scale);
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+inline size_t interp_smem_bytes(int cs_stride)
+{
+    return spread_smem_bytes(cs_stride) + (size_t)NWARP * BATCH * PART_LD * sizeof(u64);
+}
+
+}  // namespace cs
+}  // namespace nufft

@@ -1,0 +1,293 @@
+// cs_spread.cuh — K-spread, column-streaming variant (3-D, HalfSupport(4), ComplexF32): no shared-memory tile at all.
+// Replaces src/spreading/gpu.jl:237-434 for this configuration class (same sums, different order).
+//
+// set_points orders the points by (z segment of 64 cells, column of 4 x 4 cells in (x, y), layer of 4 cells in z).  A
+// warp walks through a chunk of that order.  All points of a column touch the same padded (x, y) footprint of 11 x 11
+// cells, and consecutive layers overlap in 7 of their 11 z planes, so the warp keeps the footprint of the CURRENT layer
+// (11 x 11 x 11 cells) in registers — lane L owns the columns rt::lane_slots(L), 4 columns x 11 planes = 44 packed
+// (re, im) accumulators — and slides it upwards:
+//   per point   8 shared-memory loads of the point's record (zero-padded 1-D weights, value), 6 FMUL2 and 44 FFMA2 per
+//               lane: a_k = value x wx x wy for the lane's 4 columns, G[k][i] += a_k x wz[i].  Branch-free;
+//   next layer  the 4 lowest planes are final for this warp: 16 red.global.add.v2.f32 per lane (rows of 11 consecutive
+//               cells), the other 7 planes move down in the register file, 4 fresh planes start at zero.  About once per
+//               8 points at one point per 8 fine cells;
+//   new column / end of chunk   the whole window is added to the grid (44 reductions per lane) and restarts at zero.
+// Partial sums of different warps meet only in global memory (L2 reductions); the chunk order keeps the set of
+// concurrently active columns inside a slab of a few MB, so they meet in L2.  The kernel values are evaluated by 3 lanes
+// per point (one per dimension, batches of 10 points) into a warp-private record.  Shared memory holds only records and
+// the coefficient tables, so residency is bounded by registers (8 warps per SM).
+#pragma once
+#include "rt_common.cuh"
+#include "spread.cuh"
+
+namespace nufft {
+namespace cs {
+
+using rt::u64;
+using rt::pk2;
+using rt::unpk2;
+using rt::fmul2;
+using rt::ffma2;
+using rt::P;
+
+constexpr int M = 4, W = 8;
+constexpr int COL = 4;                    // column edge in x, y and layer thickness in z (cells)
+constexpr int SEG = 64;                   // z segment (cells): bins are 4 x 4 x 64 cells, 16 layers each
+constexpr int NWARP = 8;                  // warps per CTA (one CTA per SM)
+constexpr int BATCH = 10;                 // points per evaluation batch: 3 lanes per point
+constexpr int CHUNK = 240;                // points per work item
+constexpr int REC_F = 52;                 // floats per point record
+constexpr int OFF_WX = 0;                 // [0..11]  wx_pad[0..10], 0
+constexpr int OFF_HV = 12;                // [12..13] value (re, im) [spreading]
+constexpr int OFF_WY = rt::OFF_WY;        // [16..39] wyT rows (rt::store_y)
+constexpr int OFF_WZ = 40;                // [40..51] wz_pad[0..10], 0
+static_assert(OFF_WY == 16, "record layout shared with rt_common.cuh");
+
+// per-lane kernel parameters of ONE dimension (lane = 3 * point + dimension)
+__device__ __forceinline__ KernelParams<float> lane_kernel_params(const KernelParams<float> &kp, int d)
+{
+    KernelParams<float> kl = kp;
+    kl.N[0] = d == 0 ? kp.N[0] : (d == 1 ? kp.N[1] : kp.N[2]);
+    kl.beta[0] = d == 0 ? kp.beta[0] : (d == 1 ? kp.beta[1] : kp.beta[2]);
+    kl.tau[0] = d == 0 ? kp.tau[0] : (d == 1 ? kp.tau[1] : kp.tau[2]);
+    kl.dx[0] = d == 0 ? kp.dx[0] : (d == 1 ? kp.dx[1] : kp.dx[2]);
+    return kl;
+}
+
+// 2M = 8 kernel values of one dimension; the piecewise-polynomial fast path reads the coefficient rows as two 16-byte
+// vectors (same fmaf sequence as eval_kernel_values, bit-identical values)
+__device__ __forceinline__ int eval_m4(const KernelParams<float> &kl, const float *cs, float x, float (&w)[W])
+{
+    if (kl.mode == NUFFT_EVAL_FAST && kl.kind != NUFFT_KERNEL_BSPLINE && kl.kind != NUFFT_KERNEL_GAUSSIAN) {
+        float r;
+        const int i0 = point_to_cell0<float>(x, kl.N[0], r);
+        const float xt = 2.f * (r - (float)i0) - 1.f;
+        const float4 *c4 = reinterpret_cast<const float4 *>(cs);
+        float4 a = c4[2 * (M + 3)], b = c4[2 * (M + 3) + 1];
+#pragma unroll
+        for (int p = M + 2; p >= 0; --p) {
+            const float4 ca = c4[2 * p], cb = c4[2 * p + 1];
+            a.x = fmaf(xt, a.x, ca.x); a.y = fmaf(xt, a.y, ca.y); a.z = fmaf(xt, a.z, ca.z); a.w = fmaf(xt, a.w, ca.w);
+            b.x = fmaf(xt, b.x, cb.x); b.y = fmaf(xt, b.y, cb.y); b.z = fmaf(xt, b.z, cb.z); b.w = fmaf(xt, b.w, cb.w);
+        }
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        return i0;
+    }
+    return eval_kernel_values<float, M>(kl, cs, 0, x, w);
+}
+
+__device__ __forceinline__ void red_cell(float2 *p, u64 v)
+{
+    const float2 f = unpk2(v);
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(f.x), "f"(f.y) : "memory");
+}
+
+template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
+__global__ void __launch_bounds__(32 * NWARP)       // (no min-blocks hint: with it ptxas renames the accumulators and adds ~30 MOVs per point)
+cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__restrict__ perm, int32_t *work_counter,
+                 const float *__restrict__ xs0, const float *__restrict__ xs1, const float *__restrict__ xs2, PtrPack vp, int C,
+                 float2 *__restrict__ us, int64_t ncells, const float *__restrict__ nu_weights)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH][REC_F]
+    float *cs_s = rec_all + NWARP * BATCH * REC_F;                           // [3][cs_stride]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    float *rec_w = rec_all + warp * BATCH * REC_F;
+
+    for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
+    __syncthreads();                                   // the only CTA barrier: coefficient tables
+
+    const rt::LaneSlots ls = rt::lane_slots(lane);
+    const int ep = lane / 3, ed = lane - 3 * ep;       // evaluation role: lane = 3 * point + dimension
+    const bool elane = lane < 3 * BATCH;
+    const float *xs_d = ed == 0 ? xs0 : (ed == 1 ? xs1 : xs2);
+    const KernelParams<float> kl = lane_kernel_params(kp, ed);
+    const float *cs_d = cs_s + ed * kp.cs_stride;
+    const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
+    const int plane = Nx * Ny;
+
+    u64 G[4][P];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < P; ++i) G[k][i] = 0ull;
+
+    while (true) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1);
+        item = __shfl_sync(FULL, item, 0);
+        const int64_t k0l = (int64_t)item * CHUNK;
+        if (k0l >= np) break;
+        const int k0 = (int)k0l, k1 = min(k0 + CHUNK, np);
+        const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
+
+        for (int c = 0; c < C; ++c) {
+            const float2 *vc = (const float2 *)vp.p[c];
+            float2 *u = us + (int64_t)c * ncells;
+            // ---- window state ---------------------------------------------------------------------------------------
+            int wcol = -1, wl = 0;                         // column id (cy << 16 | cx), layer
+            int goff[4] = {0, 0, 0, 0};                    // cell offsets of the lane's 4 columns inside a z plane
+
+            auto flush_planes = [&](auto i0c, auto i1c) {  // planes [i0, i1) of the window -> grid
+                constexpr int I0 = decltype(i0c)::value, I1 = decltype(i1c)::value;
+#pragma unroll
+                for (int i = I0; i < I1; ++i) {
+                    const int gz = wrap1(COL * wl - (M - 1) + i, Nz);
+                    float2 *pl = u + (int64_t)gz * plane;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) red_cell(pl + goff[k], G[k][i]);
+                    if (ls.has3) red_cell(pl + goff[3], G[3][i]);
+                }
+            };
+            auto flush_all = [&]() {
+                flush_planes(std::integral_constant<int, 0>{}, std::integral_constant<int, P>{});
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int i = 0; i < P; ++i) G[k][i] = 0ull;
+            };
+            auto shift_one = [&]() {                       // next layer: retire 4 planes, slide the other 7 down
+                flush_planes(std::integral_constant<int, 0>{}, std::integral_constant<int, COL>{});
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int i = 0; i < P - COL; ++i) G[k][i] = G[k][i + COL];
+#pragma unroll
+                    for (int i = P - COL; i < P; ++i) G[k][i] = 0ull;
+                }
+                ++wl;
+            };
+
+            // ---- software pipeline of the global loads: perm two batches ahead, coordinate / value one batch ahead --------
+            auto load_n = [&](int bi) -> int32_t {
+                const int k = k0 + bi * BATCH + ep;
+                return (elane && ed == 2 && k < k1) ? perm[k] : 0;
+            };
+            auto load_x = [&](int bi) -> float {
+                const int k = k0 + bi * BATCH + ep;
+                return (elane && k < k1) ? xs_d[k] : 0.f;
+            };
+            auto load_v = [&](int bi, int32_t n) -> float2 {
+                const int k = k0 + bi * BATCH + ep;
+                return (elane && ed == 2 && k < k1) ? vc[n] : make_float2(0.f, 0.f);
+            };
+            auto load_w = [&](int bi, int32_t n) -> float {          // non-uniform callback weight (original index)
+                const int k = k0 + bi * BATCH + ep;
+                return (nu_weights && elane && ed == 2 && k < k1) ? nu_weights[n] : 1.f;
+            };
+            int32_t n1 = load_n(0);
+            float xq = load_x(0);
+            float2 vq = load_v(0, n1);
+            float wq = load_w(0, n1);
+            n1 = load_n(1);
+
+            for (int bi = 0; bi < nbatches; ++bi) {
+                const int nb = min(BATCH, k1 - (k0 + bi * BATCH));
+                const float x = xq;
+                const float2 v = cmul(vq, wq);
+                const int32_t n2 = load_n(bi + 2);
+                xq = load_x(bi + 1);
+                vq = load_v(bi + 1, n1);
+                wq = load_w(bi + 1, n1);
+                n1 = n2;
+
+                // ---- evaluate: 3 lanes per point -----------------------------------------------------------------
+                const bool act = elane && ep < nb;
+                int cell = 0;
+                if (act) {
+                    float *r = rec_w + ep * REC_F;
+                    float w[W], pw[P];
+                    cell = eval_m4(kl, cs_d, x, w);
+                    rt::pad_shift(w, cell & 3, pw);
+                    if (ed == 1) {
+                        rt::store_y(r, pw);
+                    } else {
+                        float4 *q = reinterpret_cast<float4 *>(r + (ed == 0 ? OFF_WX : OFF_WZ));
+                        q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+                        q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+                        q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
+                    }
+                }
+                int mycol, mylay;                          // lane p < nb: column id and layer of point p of the batch
+                {
+                    const int src = min(3 * ep, 27);
+                    const int c0 = __shfl_sync(FULL, cell, src), c1 = __shfl_sync(FULL, cell, src + 1);
+                    const int col = ((c1 >> 2) << 16) | (c0 >> 2);
+                    if (act && ed == 2)
+                        *reinterpret_cast<float2 *>(rec_w + ep * REC_F + OFF_HV) = v;
+                    const int from = min(3 * lane + 2, 31);
+                    mycol = __shfl_sync(FULL, col, from);
+                    mylay = __shfl_sync(FULL, cell >> 2, from);
+                }
+                // runs of points sharing the window: bit p of `starts` is set when point p opens a new (column, layer)
+                unsigned starts;
+                {
+                    const int pc = __shfl_up_sync(FULL, mycol, 1), pl = __shfl_up_sync(FULL, mylay, 1);
+                    starts = __ballot_sync(FULL, lane < nb && (lane == 0 || mycol != pc || mylay != pl));
+                }
+                __syncwarp();
+
+                // ---- accumulate --------------------------------------------------------------------------------------
+                for (int p0 = 0; p0 < nb;) {
+                    const unsigned rest = starts & ~((2u << p0) - 1u);       // run starts after p0
+                    const int p1 = rest ? __ffs(rest) - 1 : nb;
+                    const int col = __shfl_sync(FULL, mycol, p0), lay = __shfl_sync(FULL, mylay, p0);
+                    if (col != wcol || lay != wl) {                           // move the window (cold path)
+                        const int d = lay - wl;
+                        if (col == wcol && d > 0 && d < 3) {
+                            shift_one();
+                            if (d == 2) shift_one();
+                        } else {
+                            if (wcol >= 0) flush_all();
+                            wcol = col;
+                            wl = lay;
+                            const int cx = col & 0xffff, cy = col >> 16;
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                                goff[k] = wrap1(COL * cy - (M - 1) + ls.g + 3 * k, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                            goff[3] = wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx);
+                        }
+                    }
+                    // hot loop: the points of the run only touch registers
+#pragma unroll 1
+                    for (int p = p0; p < p1; ++p) {
+                        const float *r = rec_w + p * REC_F;
+                        const float2 hv = *reinterpret_cast<const float2 *>(r + OFF_HV);
+                        const float4 wy = *reinterpret_cast<const float4 *>(r + OFF_WY + 4 * ls.row);
+                        const float wx = r[OFF_WX + ls.x], wx3 = r[OFF_WX + ls.x3];
+                        const float4 *zq = reinterpret_cast<const float4 *>(r + OFF_WZ);
+                        const float4 z0 = zq[0], z1 = zq[1], z2 = zq[2];
+                        const u64 w01 = fmul2(pk2(wx, wx), pk2(wy.x, wy.y));
+                        const u64 w23 = fmul2(pk2(wx, wx3), pk2(wy.z, wy.w));
+                        const float2 wa = unpk2(w01), wb = unpk2(w23);
+                        const u64 v2 = pk2(hv.x, hv.y);
+                        const u64 a0 = fmul2(v2, pk2(wa.x, wa.x)), a1 = fmul2(v2, pk2(wa.y, wa.y));
+                        const u64 a2 = fmul2(v2, pk2(wb.x, wb.x)), a3 = fmul2(v2, pk2(wb.y, wb.y));
+                        const float wz[P] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w, z2.x, z2.y, z2.z};
+#pragma unroll
+                        for (int i = 0; i < P; ++i) {
+                            const u64 wzz = pk2(wz[i], wz[i]);
+                            G[0][i] = ffma2(a0, wzz, G[0][i]);
+                            G[1][i] = ffma2(a1, wzz, G[1][i]);
+                            G[2][i] = ffma2(a2, wzz, G[2][i]);
+                            G[3][i] = ffma2(a3, wzz, G[3][i]);
+                        }
+                    }
+                    p0 = p1;
+                }
+                __syncwarp();
+            }
+            if (wcol >= 0) flush_all();
+        }
+    }
+}
+
+inline size_t spread_smem_bytes(int cs_stride)
+{
+    return (size_t)NWARP * BATCH * REC_F * sizeof(float) + (size_t)(3 * cs_stride + 4) * sizeof(float) + 16;
+}
+
+}  // namespace cs
+}  // namespace nufft

@@ -276,6 +276,63 @@ static bool choose_geometry(Plan &p)
     g.sub[0] = g.sub[1] = g.sub[2] = 1;
     g.nsub = 1;
 
+    // ---- column-streaming fast path (cs_spread.cuh / cs_interp.cuh): D = 3, M = 4, ComplexF32 -----------------------
+    // bins = columns of 4 x 4 cells in (x, y), segments of up to 64 cells in z; the sort key is refined by the layer
+    // (4 cells in z) inside the segment, so the points of a column arrive bottom to top
+    {
+        bool cs = D == 3 && M == 4 && !p.f64 && p.cplx && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
+        if (const char *e = getenv("NUFFT_B200_CS")) cs = cs && atoi(e) != 0;
+        for (int d = 0; d < D && cs; ++d)
+            if (p.Nos[d] < 16 || p.Nos[d] > 65536 * 4) cs = false;
+        if (p.Nos[0] * p.Nos[1] * p.Nos[2] >= ((int64_t)1 << 31)) cs = false;        // 32-bit cell offsets
+        if (cs) {
+            g.rt = 3;
+            int Bc[3] = {4, 4, (int)std::min<int64_t>(64, bcap(2)) / 4 * 4};
+            tile_bytes(Bc, T, S);               // strides of the generic shared-memory kernels (unused on this path)
+            int64_t nbins = 1;
+            for (int d = 0; d < 3; ++d) {
+                g.B[d] = Bc[d]; g.T[d] = T[d]; g.S[d] = S[d];
+                g.sub[d] = d < 2 ? 1 : Bc[2] / 4;
+                g.nb[d] = (int)cdiv(p.Nos[d], Bc[d]);
+                nbins *= g.nb[d];
+            }
+            g.nsub = g.sub[2];
+            g.tile_cells = S[0] * T[1] * T[2];
+            p.nbins = nbins;
+            p.key_bits = 1;
+            while (((int64_t)1 << p.key_bits) < nbins * g.nsub) ++p.key_bits;
+            return true;
+        }
+    }
+
+    // ---- warp-private-tile fast path (wp_spread.cuh / wp_interp.cuh): D = 3, M = 4, ComplexF32 --------------------
+    // bins of 8 x 8 x 8 cells = 2 x 2 x 2 sub-bins of 4 x 4 x 4 cells; the sort key is refined by the sub-bin
+    {
+        bool wp = D == 3 && M == 4 && !p.f64 && p.cplx && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
+        if (const char *e = getenv("NUFFT_B200_WP")) wp = wp && atoi(e) != 0;
+        else wp = wp && NUFFT_WP_DEFAULT;
+        for (int d = 0; d < D && wp; ++d)
+            if (p.Nos[d] < 16 || (p.Nos[d] & 1)) wp = false;
+        if (wp) {
+            g.rt = 2;
+            int Bw[3] = {8, 8, 8};
+            tile_bytes(Bw, T, S);               // strides of the generic shared-memory kernels (fallbacks)
+            int64_t nbins = 1;
+            for (int d = 0; d < 3; ++d) {
+                g.B[d] = 8; g.T[d] = T[d]; g.S[d] = S[d];
+                g.sub[d] = 2;
+                g.nb[d] = (int)cdiv(p.Nos[d], 8);
+                nbins *= g.nb[d];
+            }
+            g.nsub = 8;
+            g.tile_cells = S[0] * T[1] * T[2];
+            p.nbins = nbins;
+            p.key_bits = 1;
+            while (((int64_t)1 << p.key_bits) < nbins * g.nsub) ++p.key_bits;
+            return true;
+        }
+    }
+
     // ---- register-window fast path (rt_spread.cuh / rt_interp.cuh): D = 3, M = 4, Float32 ----------------------
     // bins of 16 x 16 cells in (x, y) (4 x 4 columns of 4 x 4 cells) and Bz cells along z, Bz chosen so that two CTAs
     // (tile + point records) are resident per SM; the sort key is refined by (column, z cell)

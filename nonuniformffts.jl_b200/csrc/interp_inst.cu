@@ -4,6 +4,8 @@
 #include <type_traits>
 #include "interp.cuh"
 #include "rt_interp.cuh"
+#include "wp_interp.cuh"
+#include "cs_interp.cuh"
 
 #ifndef INST_T
 #define INST_T float
@@ -31,8 +33,35 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
         MutPtrPack pack{};
         for (int c = 0; c < cn; ++c) pack.p[c] = vp[c0 + c];
         const Cell *us = (const Cell *)p.d_us + (int64_t)c0 * p.ncells;
+        if constexpr (std::is_same<T, float>::value && CPLX && D == 3 && M == 4) {
+            if (p.geom.rt == 3 && p.method == NUFFT_METHOD_SHARED_MEMORY) {
+                auto kern = cs::cs_interp_kernel<void>;
+                const size_t smem = cs::interp_smem_bytes(p.cs_stride);
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int nsm = 0;
+                CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
+                kern<<<nsm, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, p.d_perm, p.d_counters, xs0, xs1, xs2, pack, cn, us,
+                                                        p.ncells, prefactor, nuw);
+                NUFFT_COUNT_LAUNCH();
+                continue;
+            }
+            if (p.geom.rt == 2 && p.method == NUFFT_METHOD_SHARED_MEMORY) {
+                auto kern = wp::wp_interp_kernel<void>;
+                const size_t smem = wp::interp_smem_bytes(p.cs_stride);
+                const int nthreads = 32 * wp::NWARP;
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int nsm = 0;
+                CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+                SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
+                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
+                kern<<<nsm, nthreads, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, prefactor, nuw);
+                NUFFT_COUNT_LAUNCH();
+                continue;
+            }
+        }
         if constexpr (std::is_same<T, float>::value && D == 3 && M == 4) {
-            if (p.geom.rt && p.method == NUFFT_METHOD_SHARED_MEMORY) {
+            if (p.geom.rt == 1 && p.method == NUFFT_METHOD_SHARED_MEMORY) {
                 auto kern = rt::rt_interp_kernel<CPLX>;
                 const size_t smem = rt::interp_smem_bytes(p.geom, p.cs_stride, sizeof(Cell));
                 const int nthreads = 32 * rt::INTERP_NW;

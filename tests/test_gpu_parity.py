@@ -39,17 +39,19 @@ def run_case(nufft, oracle_mod, dtype, dims, Np, *, m=4, sigma=2.0, kernel="back
     _, cum_o, perm_o = op.sort_points(xs, bdims)
     assert np.array_equal(off.cpu().numpy(), cum_o), "bin offsets differ from the oracle"
     assert np.array_equal(perm.cpu().numpy(), perm_o), "permutation differs from the oracle (stable order)"
-    # the order the kernels use: plans on the register-window fast path refine the bins into columns of 4 x 4 cells
-    # and single cells along z; expected = stable sort by (bin, column, z cell) of the oracle's own cell indices
+    # the order the kernels use: plans on the warp-private-tile / register-window fast paths refine the bins into
+    # sub-bins of 4 x 4 x 4 / 4 x 4 x 1 cells; expected = stable sort by (bin, sub-bin) of the oracle's own cell indices
     fperm, foff, sub = gp.binning_fine()
     if sub != (1, 1, 1):
-        assert D == 3 and bdims[0] % 4 == 0 and bdims[1] % 4 == 0 and sub == (bdims[0] // 4, bdims[1] // 4, bdims[2])
+        assert D == 3 and all(bdims[d] % sub[d] == 0 for d in range(3))
+        sw = [bdims[d] // sub[d] for d in range(3)]        # sub-bin edge: (4, 4, 1) register-window, (4, 4, 4) warp-private
+        assert sw in ([4, 4, 1], [4, 4, 4])
         cell, _, _ = op.sort_points(xs, (1, 1, 1))
         cell = cell.astype(np.int64)
         c = [cell % op.Nos[0], (cell // op.Nos[0]) % op.Nos[1], cell // (op.Nos[0] * op.Nos[1])]
         nb = [-(-n // b) for n, b in zip(op.Nos, bdims)]
         bb = [c[d] // bdims[d] for d in range(3)]
-        ss = [(c[0] - bb[0] * bdims[0]) // 4, (c[1] - bb[1] * bdims[1]) // 4, c[2] - bb[2] * bdims[2]]
+        ss = [(c[d] - bb[d] * bdims[d]) // sw[d] for d in range(3)]
         key = ((bb[2] * nb[1] + bb[1]) * nb[0] + bb[0]) * (sub[0] * sub[1] * sub[2]) + (ss[1] * sub[0] + ss[0]) * sub[2] + ss[2]
         assert np.array_equal(fperm.cpu().numpy(), np.argsort(key, kind="stable").astype(np.int32)), "fine permutation"
         assert foff is None
