@@ -10,8 +10,9 @@
 //   per batch   3 lanes per point add up the 32 partials of that point (11 LDS.64 each, rows padded to 35 -> no bank
 //               conflicts) + 2 shuffles; prefactor, non-uniform callback, scatter through the permutation;
 //   next layer  7 planes move down in the register file; the 4 new planes were requested from global memory (L2) when
-//               the window arrived at the CURRENT layer (16 loads per lane into spare registers), so their latency is
-//               covered by the ~8 points of the layer;
+//               the window arrived at the CURRENT layer (16 cp.async per lane into a warp-private staging buffer, so no
+//               registers and no scoreboard shared with other loads), their latency is covered by the ~8 points of
+//               the layer; 16 LDS.64 bring them in;
 //   new column  44 loads per lane (rows of 11 consecutive cells).
 #pragma once
 #include "cs_spread.cuh"
@@ -55,12 +56,14 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH][REC_F]
     u64 *part_all = (u64 *)(rec_all + NWARP * BATCH * REC_F);                // [NWARP][BATCH][PART_LD] lane partials
-    float *cs_s = (float *)(part_all + NWARP * BATCH * PART_LD);             // [3][cs_stride]
+    u64 *stage_all = part_all + NWARP * BATCH * PART_LD;                     // [NWARP][4 planes x 4 columns][32 lanes]
+    float *cs_s = (float *)(stage_all + NWARP * 16 * 32);                    // [3][cs_stride]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     float *rec_w = rec_all + warp * BATCH * REC_F;
     u64 *part_w = part_all + warp * BATCH * PART_LD;
+    u64 *stage_w = stage_all + warp * 16 * 32 + lane;
 
     for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
     __syncthreads();                                   // the only CTA barrier: coefficient tables
@@ -75,14 +78,10 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
     const int plane = Nx * Ny;
 
     u64 G[4][P];                                       // window: planes COL * wl - 3 .. COL * wl + 7
-    u64 H[4][COL];                                     // the 4 planes above it, requested ahead
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int i = 0; i < P; ++i) G[k][i] = 0ull;
-#pragma unroll
-        for (int i = 0; i < COL; ++i) H[k][i] = 0ull;
-    }
 
     while (true) {
         int item = 0;
@@ -104,10 +103,12 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                 for (int i = 0; i < COL; ++i) {
                     const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + P + i, Nz) * plane;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) H[k][i] = ldg_cell(pl + goff[k]);
+                    for (int k = 0; k < 4; ++k) cp_async_cell<8>(stage_w + (4 * i + k) * 32, pl + goff[k]);
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             };
             auto load_all = [&]() {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");     // a request of the previous window may be in flight
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + i, Nz) * plane;
@@ -117,12 +118,13 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                 request_ahead();
             };
             auto shift_one = [&]() {                       // next layer: 7 planes slide down, the requested 4 come in
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
                     for (int i = 0; i < P - COL; ++i) G[k][i] = G[k][i + COL];
 #pragma unroll
-                    for (int i = 0; i < COL; ++i) G[k][P - COL + i] = H[k][i];
+                    for (int i = 0; i < COL; ++i) G[k][P - COL + i] = stage_w[(4 * i + k) * 32];
                 }
                 ++wl;
                 request_ahead();
@@ -134,15 +136,20 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                 return (elane && k < k1) ? xs_d[k] : 0.f;
             };
             xq = load_x(0);
+            auto load_n = [&](int bi) -> int32_t {
+                const int k = k0 + bi * BATCH + lane;
+                return (lane < BATCH && k < k1) ? perm[k] : 0;
+            };
+            int32_t n_nxt = load_n(0);
 
             for (int bi = 0; bi < nbatches; ++bi) {
                 const int kb = k0 + bi * BATCH;
                 const int nb = min(BATCH, k1 - kb);
                 const float x = xq;
                 xq = load_x(bi + 1);
-                // original index (and callback weight) of the point this lane will store (lanes 0 .. nb - 1)
-                int32_t n_out = 0;
-                if (lane < nb) n_out = perm[kb + lane];
+                // original index of the point this lane will store (lanes 0 .. nb - 1): requested one batch ahead
+                const int32_t n_out = n_nxt;
+                n_nxt = load_n(bi + 1);
 
                 // ---- evaluate: 3 lanes per point -----------------------------------------------------------------
                 const bool act = elane && ep < nb;
@@ -172,8 +179,16 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                 }
                 __syncwarp();
 
-                for (int p = 0; p < nb; ++p) {
-                    const int col = __shfl_sync(FULL, mycol, p), lay = __shfl_sync(FULL, mylay, p);
+                // runs of points sharing the window: bit p of `starts` is set when point p opens a new (column, layer)
+                unsigned starts;
+                {
+                    const int pc = __shfl_up_sync(FULL, mycol, 1), pl = __shfl_up_sync(FULL, mylay, 1);
+                    starts = __ballot_sync(FULL, lane < nb && (lane == 0 || mycol != pc || mylay != pl));
+                }
+                for (int p0 = 0; p0 < nb;) {
+                    const unsigned rest = starts & ~((2u << p0) - 1u);       // run starts after p0
+                    const int p1 = rest ? __ffs(rest) - 1 : nb;
+                    const int col = __shfl_sync(FULL, mycol, p0), lay = __shfl_sync(FULL, mylay, p0);
                     if (col != wcol || lay != wl) {        // move the window (cold path)
                         const int d = lay - wl;
                         if (col == wcol && d == 1) {
@@ -189,27 +204,29 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                             load_all();
                         }
                     }
-                    const float *r = rec_w + p * REC_F;
-                    const float4 wy = *reinterpret_cast<const float4 *>(r + OFF_WY + 4 * ls.row);
-                    const float wx = r[OFF_WX + ls.x], wx3 = r[OFF_WX + ls.x3];
-                    const float4 *zq = reinterpret_cast<const float4 *>(r + OFF_WZ);
-                    const float4 z0 = zq[0], z1 = zq[1], z2 = zq[2];
-                    const float wz[P] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w, z2.x, z2.y, z2.z};
-                    u64 tk[4] = {0ull, 0ull, 0ull, 0ull};
+                    // hot loop (rotated: the next record is requested at the end of the body)
+                    PointRec A = load_rec(rec_w + p0 * REC_F, ls);
+#pragma unroll 1
+                    for (int p = p0; p < p1; ++p) {
+                        const float wz[P] = {A.z0.x, A.z0.y, A.z0.z, A.z0.w, A.z1.x, A.z1.y, A.z1.z, A.z1.w, A.z2.x, A.z2.y, A.z2.z};
+                        u64 tk[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-                    for (int i = 0; i < P; ++i) {
-                        const u64 wzz = pk2(wz[i], wz[i]);
+                        for (int i = 0; i < P; ++i) {
+                            const u64 wzz = pk2(wz[i], wz[i]);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][i], wzz, tk[k]);
+                            for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][i], wzz, tk[k]);
+                        }
+                        const u64 w01 = fmul2(pk2(A.wx, A.wx), pk2(A.wy.x, A.wy.y));
+                        const u64 w23 = fmul2(pk2(A.wx, A.wx3), pk2(A.wy.z, A.wy.w));
+                        const float2 wa = unpk2(w01), wb = unpk2(w23);
+                        u64 acc = fmul2(tk[0], pk2(wa.x, wa.x));
+                        acc = ffma2(tk[1], pk2(wa.y, wa.y), acc);
+                        acc = ffma2(tk[2], pk2(wb.x, wb.x), acc);
+                        acc = ffma2(tk[3], pk2(wb.y, wb.y), acc);
+                        part_w[p * PART_LD + lane] = acc;
+                        A = load_rec(rec_w + min(p + 1, p1 - 1) * REC_F, ls);
                     }
-                    const u64 w01 = fmul2(pk2(wx, wx), pk2(wy.x, wy.y));
-                    const u64 w23 = fmul2(pk2(wx, wx3), pk2(wy.z, wy.w));
-                    const float2 wa = unpk2(w01), wb = unpk2(w23);
-                    u64 acc = fmul2(tk[0], pk2(wa.x, wa.x));
-                    acc = ffma2(tk[1], pk2(wa.y, wa.y), acc);
-                    acc = ffma2(tk[2], pk2(wb.x, wb.x), acc);
-                    acc = ffma2(tk[3], pk2(wb.y, wb.y), acc);
-                    part_w[p * PART_LD + lane] = acc;
+                    p0 = p1;
                 }
                 __syncwarp();
                 // ---- per batch: lanes 3p, 3p + 1, 3p + 2 add up the 32 lane partials of point p -------------------------
@@ -235,7 +252,7 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
 
 inline size_t interp_smem_bytes(int cs_stride)
 {
-    return spread_smem_bytes(cs_stride) + (size_t)NWARP * BATCH * PART_LD * sizeof(u64);
+    return spread_smem_bytes(cs_stride) + (size_t)NWARP * (BATCH * PART_LD + 16 * 32) * sizeof(u64);
 }
 
 }  // namespace cs

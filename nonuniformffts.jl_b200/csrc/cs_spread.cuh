@@ -15,7 +15,7 @@
 // Partial sums of different warps meet only in global memory (L2 reductions); the chunk order keeps the set of
 // concurrently active columns inside a slab of a few MB, so they meet in L2.  The kernel values are evaluated by 3 lanes
 // per point (one per dimension, batches of 10 points) into a warp-private record.  Shared memory holds only records and
-// the coefficient tables, so residency is bounded by registers (8 warps per SM).
+// the coefficient tables, so residency is bounded by registers (12 warps per SM).
 #pragma once
 #include "rt_common.cuh"
 #include "spread.cuh"
@@ -32,8 +32,8 @@ using rt::P;
 
 constexpr int M = 4, W = 8;
 constexpr int COL = 4;                    // column edge in x, y and layer thickness in z (cells)
-constexpr int SEG = 64;                   // z segment (cells): bins are 4 x 4 x 64 cells, 16 layers each
-constexpr int NWARP = 8;                  // warps per CTA (one CTA per SM)
+constexpr int SEG = 256;                  // z segment (cells): bins are 4 x 4 x SEG cells, SEG / 4 layers each
+constexpr int NWARP = 12;                 // warps per CTA (one CTA per SM): 168 registers per thread
 constexpr int BATCH = 10;                 // points per evaluation batch: 3 lanes per point
 constexpr int CHUNK = 240;                // points per work item
 constexpr int REC_F = 52;                 // floats per point record
@@ -80,6 +80,43 @@ __device__ __forceinline__ void red_cell(float2 *p, u64 v)
 {
     const float2 f = unpk2(v);
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(f.x), "f"(f.y) : "memory");
+}
+
+struct PointRec {
+    float2 hv;
+    float4 wy;
+    float wx, wx3;
+    float4 z0, z1, z2;
+};
+__device__ __forceinline__ PointRec load_rec(const float *r, const rt::LaneSlots &ls)
+{
+    PointRec q;
+    q.hv = *reinterpret_cast<const float2 *>(r + OFF_HV);
+    q.wy = *reinterpret_cast<const float4 *>(r + OFF_WY + 4 * ls.row);
+    q.wx = r[OFF_WX + ls.x];
+    q.wx3 = r[OFF_WX + ls.x3];
+    const float4 *zq = reinterpret_cast<const float4 *>(r + OFF_WZ);
+    q.z0 = zq[0]; q.z1 = zq[1]; q.z2 = zq[2];
+    return q;
+}
+// G[k][i] += value x (wx wy)_k x wz_i : 6 FMUL2 + 44 FFMA2
+__device__ __forceinline__ void accumulate(u64 (&G)[4][P], const PointRec &q)
+{
+    const u64 w01 = fmul2(pk2(q.wx, q.wx), pk2(q.wy.x, q.wy.y));
+    const u64 w23 = fmul2(pk2(q.wx, q.wx3), pk2(q.wy.z, q.wy.w));
+    const float2 wa = unpk2(w01), wb = unpk2(w23);
+    const u64 v2 = pk2(q.hv.x, q.hv.y);
+    const u64 a0 = fmul2(v2, pk2(wa.x, wa.x)), a1 = fmul2(v2, pk2(wa.y, wa.y));
+    const u64 a2 = fmul2(v2, pk2(wb.x, wb.x)), a3 = fmul2(v2, pk2(wb.y, wb.y));
+    const float wz[P] = {q.z0.x, q.z0.y, q.z0.z, q.z0.w, q.z1.x, q.z1.y, q.z1.z, q.z1.w, q.z2.x, q.z2.y, q.z2.z};
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const u64 wzz = pk2(wz[i], wz[i]);
+        G[0][i] = ffma2(a0, wzz, G[0][i]);
+        G[1][i] = ffma2(a1, wzz, G[1][i]);
+        G[2][i] = ffma2(a2, wzz, G[2][i]);
+        G[3][i] = ffma2(a3, wzz, G[3][i]);
+    }
 }
 
 template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
@@ -250,30 +287,13 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                             goff[3] = wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx);
                         }
                     }
-                    // hot loop: the points of the run only touch registers
+                    // hot loop: the points of the run only touch registers.  Rotated: the record of the next point is
+                    // requested at the end of the body, into the registers the current one has just released
+                    PointRec A = load_rec(rec_w + p0 * REC_F, ls);
 #pragma unroll 1
                     for (int p = p0; p < p1; ++p) {
-                        const float *r = rec_w + p * REC_F;
-                        const float2 hv = *reinterpret_cast<const float2 *>(r + OFF_HV);
-                        const float4 wy = *reinterpret_cast<const float4 *>(r + OFF_WY + 4 * ls.row);
-                        const float wx = r[OFF_WX + ls.x], wx3 = r[OFF_WX + ls.x3];
-                        const float4 *zq = reinterpret_cast<const float4 *>(r + OFF_WZ);
-                        const float4 z0 = zq[0], z1 = zq[1], z2 = zq[2];
-                        const u64 w01 = fmul2(pk2(wx, wx), pk2(wy.x, wy.y));
-                        const u64 w23 = fmul2(pk2(wx, wx3), pk2(wy.z, wy.w));
-                        const float2 wa = unpk2(w01), wb = unpk2(w23);
-                        const u64 v2 = pk2(hv.x, hv.y);
-                        const u64 a0 = fmul2(v2, pk2(wa.x, wa.x)), a1 = fmul2(v2, pk2(wa.y, wa.y));
-                        const u64 a2 = fmul2(v2, pk2(wb.x, wb.x)), a3 = fmul2(v2, pk2(wb.y, wb.y));
-                        const float wz[P] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w, z2.x, z2.y, z2.z};
-#pragma unroll
-                        for (int i = 0; i < P; ++i) {
-                            const u64 wzz = pk2(wz[i], wz[i]);
-                            G[0][i] = ffma2(a0, wzz, G[0][i]);
-                            G[1][i] = ffma2(a1, wzz, G[1][i]);
-                            G[2][i] = ffma2(a2, wzz, G[2][i]);
-                            G[3][i] = ffma2(a3, wzz, G[3][i]);
-                        }
+                        accumulate(G, A);
+                        A = load_rec(rec_w + min(p + 1, p1 - 1) * REC_F, ls);
                     }
                     p0 = p1;
                 }

@@ -277,7 +277,7 @@ static bool choose_geometry(Plan &p)
     g.nsub = 1;
 
     // ---- column-streaming fast path (cs_spread.cuh / cs_interp.cuh): D = 3, M = 4, ComplexF32 -----------------------
-    // bins = columns of 4 x 4 cells in (x, y), segments of up to 64 cells in z; the sort key is refined by the layer
+    // bins = columns of 4 x 4 cells in (x, y), segments of up to 256 cells in z; the sort key is refined by the layer
     // (4 cells in z) inside the segment, so the points of a column arrive bottom to top
     {
         bool cs = D == 3 && M == 4 && !p.f64 && p.cplx && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
@@ -287,7 +287,7 @@ static bool choose_geometry(Plan &p)
         if (p.Nos[0] * p.Nos[1] * p.Nos[2] >= ((int64_t)1 << 31)) cs = false;        // 32-bit cell offsets
         if (cs) {
             g.rt = 3;
-            int Bc[3] = {4, 4, (int)std::min<int64_t>(64, bcap(2)) / 4 * 4};
+            int Bc[3] = {4, 4, (int)std::min<int64_t>(256, bcap(2)) / 4 * 4};
             tile_bytes(Bc, T, S);               // strides of the generic shared-memory kernels (unused on this path)
             int64_t nbins = 1;
             for (int d = 0; d < 3; ++d) {

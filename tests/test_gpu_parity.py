@@ -194,6 +194,33 @@ def test_empty_and_tiny(nufft, oracle_mod):
     assert float(out.abs().max()) == 0.0
 
 
+FAST_CASES = [
+    dict(dims=(35, 64, 40), Np=20000, sigma=1.5),
+    dict(dims=(32, 32, 32), Np=50000, sigma=2.0, dist="clustered"),
+    dict(dims=(16, 24, 20), Np=3000, sigma=2.0, C=2),
+    dict(dims=(40, 12, 30), Np=7000, sigma=1.25, callbacks=True, f32_relaxed=True),
+    dict(dims=(24, 24, 24), Np=9000, sigma=2.0, fftshift=True, kernel="gaussian"),
+    dict(dims=(20, 20, 20), Np=1, sigma=2.0),
+    dict(dims=(64, 64, 64), Np=300000, sigma=2.0),
+    dict(dims=(160, 16, 16), Np=40000, sigma=2.0, dist="onecell"),
+]
+
+
+@pytest.mark.parametrize("family", ["cs", "wp", "rt", "tile"])
+@pytest.mark.parametrize("case", range(len(FAST_CASES)))
+def test_fast_path_kernel_families(nufft, oracle_mod, monkeypatch, family, case):
+    """3-D, HalfSupport(4), ComplexF32: every kernel family that serves the headline configuration class — column-streaming
+    (default), warp-private tiles, register windows (both opt-in) and the generic shared-memory tiles — against the oracle,
+    including the refined sort order each of them asks set_points for."""
+    for k in ("NUFFT_B200_CS", "NUFFT_B200_WP", "NUFFT_B200_RT"):
+        monkeypatch.setenv(k, "0")
+    if family != "tile":
+        monkeypatch.setenv("NUFFT_B200_" + family.upper(), "1")
+    kw = dict(FAST_CASES[case])
+    dims, Np = kw.pop("dims"), kw.pop("Np")
+    run_case(nufft, oracle_mod, np.complex64, dims, Np, method="shared_memory", seed=3, **kw)
+
+
 @pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
 def test_pruned_fft_paths(nufft, oracle_mod, dtype):
     # power-of-two oversampled sizes -> truncating / zero-padding FFT passes fused with the deconvolution (pfft.cu);

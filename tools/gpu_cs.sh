@@ -2,14 +2,13 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-export NUFFT_B200_CS=1
-timeout 600 python tools/wp_check.py > gpurun_out/cs_check.log 2>&1
-tail -12 gpurun_out/cs_check.log
+timeout 900 python -m pytest tests -m gpu -q -x -k "fast_path or 3d_matrix or clustered" 2>&1 | tail -8 > gpurun_out/cs_tests.log
+cat gpurun_out/cs_tests.log
 timeout 300 python tools/run_c3.py --iters 3 > gpurun_out/cs_c3.log 2>&1
-tail -4 gpurun_out/cs_c3.log
-timeout 300 python tools/run_c3.py --iters 2 --dist clustered > gpurun_out/cs_c3_clustered.log 2>&1
-tail -2 gpurun_out/cs_c3_clustered.log
+tail -3 gpurun_out/cs_c3.log
 if [ "${1:-ncu}" = "ncu" ]; then
   bash tools/gpu_ncu.sh cs_spread cs_spread 0
   bash tools/gpu_ncu.sh cs_interp cs_interp 0
+  head -30 gpurun_out/cs_spread_sass.txt
+  head -30 gpurun_out/cs_interp_sass.txt
 fi
