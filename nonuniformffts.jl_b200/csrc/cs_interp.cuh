@@ -7,8 +7,8 @@
 //   per point   8 shared-memory loads of the point's record (zero-padded 1-D weights), 44 FFMA2 (t_k = sum_i G[k][i] wz[i])
 //               + 2 FMUL2 + 4 FFMA2 (sum_k t_k wx wy) per lane; the lane partial goes to a warp-private shared-memory
 //               row (one STS.64) — no dependent shuffle chain in the loop;
-//   per batch   3 lanes per point add up the 32 partials of that point (11 LDS.64 each, rows padded to 35 -> no bank
-//               conflicts) + 2 shuffles; prefactor, non-uniform callback, scatter through the permutation;
+//   per 16 pts  2 lanes per point add up the 32 partials of that point (16 LDS.64 each, rows padded to 34 -> no bank
+//               conflicts) + 1 shuffle; prefactor, non-uniform callback, scatter through the permutation;
 //   next layer  7 planes move down in the register file; the 4 new planes were requested from global memory (L2) when
 //               the window arrived at the CURRENT layer (16 cp.async per lane into a warp-private staging buffer, so no
 //               registers and no scoreboard shared with other loads), their latency is covered by the ~8 points of
@@ -38,7 +38,8 @@ __device__ __forceinline__ u64 shfl_idx_u64(u64 v, int src)
     const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
     return ((u64)hi << 32) | lo;
 }
-constexpr int PART_LD = 35;               // row length of the lane-partial buffer (u64): 35 = 3 mod 16 -> lane 3p + d reads bank pair (lane + 3j) mod 16
+constexpr int HALF = 16;                  // points per reduction round
+constexpr int PART_LD = 34;               // row length of the lane-partial buffer (u64): 34 = 2 mod 16 -> lane 2p + h reads bank pair (lane + 2j) mod 16
 
 __device__ __forceinline__ u64 ldg_cell(const float2 *p)
 {
@@ -55,25 +56,23 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH][REC_F]
-    u64 *part_all = (u64 *)(rec_all + NWARP * BATCH * REC_F);                // [NWARP][BATCH][PART_LD] lane partials
-    u64 *stage_all = part_all + NWARP * BATCH * PART_LD;                     // [NWARP][4 planes x 4 columns][32 lanes]
-    float *cs_s = (float *)(stage_all + NWARP * 16 * 32);                    // [3][cs_stride]
+    float *stage_all = rec_all + NWARP * BATCH * REC_F;                      // [NWARP][STAGE_F] coordinates / index staging
+    u64 *part_all = (u64 *)(stage_all + NWARP * STAGE_F);                    // [NWARP][HALF][PART_LD] lane partials
+    u64 *hst_all = part_all + NWARP * HALF * PART_LD;                        // [NWARP][4 planes x 4 columns][32 lanes]
+    float *cs_s = (float *)(hst_all + NWARP * 16 * 32);                      // [3][cs_stride]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     float *rec_w = rec_all + warp * BATCH * REC_F;
-    u64 *part_w = part_all + warp * BATCH * PART_LD;
-    u64 *stage_w = stage_all + warp * 16 * 32 + lane;
+    u64 *part_w = part_all + warp * HALF * PART_LD;
+    u64 *hst_w = hst_all + warp * 16 * 32 + lane;
+    float *st_x = stage_all + warp * STAGE_F + lane;                          // x, y, z at st_x[0], [32], [64]
+    int32_t *st_n = reinterpret_cast<int32_t *>(stage_all + warp * STAGE_F + 160) + lane;
 
     for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
     __syncthreads();                                   // the only CTA barrier: coefficient tables
 
     const rt::LaneSlots ls = rt::lane_slots(lane);
-    const int ep = lane / 3, ed = lane - 3 * ep;       // evaluation role: lane = 3 * point + dimension
-    const bool elane = lane < 3 * BATCH;
-    const float *xs_d = ed == 0 ? xs0 : (ed == 1 ? xs1 : xs2);
-    const KernelParams<float> kl = lane_kernel_params(kp, ed);
-    const float *cs_d = cs_s + ed * kp.cs_stride;
     const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
     const int plane = Nx * Ny;
 
@@ -103,12 +102,12 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                 for (int i = 0; i < COL; ++i) {
                     const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + P + i, Nz) * plane;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) cp_async_cell<8>(stage_w + (4 * i + k) * 32, pl + goff[k]);
+                    for (int k = 0; k < 4; ++k) cp_async_cell<8>(hst_w + (4 * i + k) * 32, pl + goff[k]);
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
+                cp_async_commit();
             };
             auto load_all = [&]() {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");     // a request of the previous window may be in flight
+                cp_async_wait0();                          // a request of the previous window may be in flight
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + i, Nz) * plane;
@@ -118,133 +117,122 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                 request_ahead();
             };
             auto shift_one = [&]() {                       // next layer: 7 planes slide down, the requested 4 come in
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                cp_async_wait0();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
                     for (int i = 0; i < P - COL; ++i) G[k][i] = G[k][i + COL];
 #pragma unroll
-                    for (int i = 0; i < COL; ++i) G[k][P - COL + i] = stage_w[(4 * i + k) * 32];
+                    for (int i = 0; i < COL; ++i) G[k][P - COL + i] = hst_w[(4 * i + k) * 32];
                 }
                 ++wl;
                 request_ahead();
             };
 
-            float xq = 0.f;
-            auto load_x = [&](int bi) -> float {
-                const int k = k0 + bi * BATCH + ep;
-                return (elane && k < k1) ? xs_d[k] : 0.f;
-            };
-            xq = load_x(0);
-            auto load_n = [&](int bi) -> int32_t {
+            // ---- global loads: one lane per point, staged through cp.async one batch ahead --------------------------------
+            auto issue_x = [&](int bi) {
                 const int k = k0 + bi * BATCH + lane;
-                return (lane < BATCH && k < k1) ? perm[k] : 0;
+                if (k < k1) {
+                    cp_async_cell<4>(st_x, xs0 + k);
+                    cp_async_cell<4>(st_x + 32, xs1 + k);
+                    cp_async_cell<4>(st_x + 64, xs2 + k);
+                    cp_async_cell<4>(st_n, perm + k);
+                }
             };
-            int32_t n_nxt = load_n(0);
+            issue_x(0);
+            cp_async_commit();
 
             for (int bi = 0; bi < nbatches; ++bi) {
                 const int kb = k0 + bi * BATCH;
                 const int nb = min(BATCH, k1 - kb);
-                const float x = xq;
-                xq = load_x(bi + 1);
-                // original index of the point this lane will store (lanes 0 .. nb - 1): requested one batch ahead
-                const int32_t n_out = n_nxt;
-                n_nxt = load_n(bi + 1);
+                cp_async_wait0();
+                const float x = st_x[0], y = st_x[32], z = st_x[64];
+                const int32_t n_mine = *st_n;              // original index of point `lane` of the batch
+                issue_x(bi + 1);
+                cp_async_commit();
 
-                // ---- evaluate: 3 lanes per point -----------------------------------------------------------------
-                const bool act = elane && ep < nb;
-                int cell = 0;
-                if (act) {
-                    float *r = rec_w + ep * REC_F;
-                    float w[W], pw[P];
-                    cell = eval_m4(kl, cs_d, x, w);
-                    rt::pad_shift(w, cell & 3, pw);
-                    if (ed == 1) {
-                        rt::store_y(r, pw);
-                    } else {
-                        float4 *q = reinterpret_cast<float4 *>(r + (ed == 0 ? OFF_WX : OFF_WZ));
-                        q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
-                        q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
-                        q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
-                    }
+                // ---- evaluate: one lane per point ----------------------------------------------------------------------
+                int mycol = -1, mylay = 0;                 // lane p < nb: column id and layer of point p of the batch
+                if (lane < nb) {
+                    int cx, cy, cz;
+                    evaluate_point(kp, cs_s, x, y, z, rec_w + lane * REC_F, cx, cy, cz);
+                    mycol = ((cy >> 2) << 16) | (cx >> 2);
+                    mylay = cz >> 2;
                 }
-                int mycol, mylay;                          // lane p < nb: column id and layer of point p of the batch
-                {
-                    const int src = min(3 * ep, 27);
-                    const int c0 = __shfl_sync(FULL, cell, src), c1 = __shfl_sync(FULL, cell, src + 1);
-                    const int col = ((c1 >> 2) << 16) | (c0 >> 2);
-                    const int from = min(3 * lane + 2, 31);
-                    mycol = __shfl_sync(FULL, col, from);
-                    mylay = __shfl_sync(FULL, cell >> 2, from);
-                }
-                __syncwarp();
-
                 // runs of points sharing the window: bit p of `starts` is set when point p opens a new (column, layer)
                 unsigned starts;
                 {
                     const int pc = __shfl_up_sync(FULL, mycol, 1), pl = __shfl_up_sync(FULL, mylay, 1);
-                    starts = __ballot_sync(FULL, lane < nb && (lane == 0 || mycol != pc || mylay != pl));
+                    starts = __ballot_sync(FULL, lane < nb && (lane == 0 || lane == HALF || mycol != pc || mylay != pl));
                 }
-                for (int p0 = 0; p0 < nb;) {
-                    const unsigned rest = starts & ~((2u << p0) - 1u);       // run starts after p0
-                    const int p1 = rest ? __ffs(rest) - 1 : nb;
-                    const int col = __shfl_sync(FULL, mycol, p0), lay = __shfl_sync(FULL, mylay, p0);
-                    if (col != wcol || lay != wl) {        // move the window (cold path)
-                        const int d = lay - wl;
-                        if (col == wcol && d == 1) {
-                            shift_one();
-                        } else {
-                            wcol = col;
-                            wl = lay;
-                            const int cx = col & 0xffff, cy = col >> 16;
+                __syncwarp();
+
+                for (int h0 = 0; h0 < nb; h0 += HALF) {    // two rounds of 16 points share the lane-partial buffer
+                    const int h1 = min(h0 + HALF, nb);
+                    for (int p0 = h0; p0 < h1;) {
+                        const unsigned rest = starts & ~((2u << p0) - 1u);       // run starts after p0
+                        const int p1 = rest ? min(__ffs(rest) - 1, h1) : h1;
+                        const int col = __shfl_sync(FULL, mycol, p0), lay = __shfl_sync(FULL, mylay, p0);
+                        if (col != wcol || lay != wl) {    // move the window (cold path)
+                            const int d = lay - wl;
+                            if (col == wcol && d == 1) {
+                                shift_one();
+                            } else {
+                                wcol = col;
+                                wl = lay;
+                                const int cx = col & 0xffff, cy = col >> 16;
 #pragma unroll
-                            for (int k = 0; k < 3; ++k)
-                                goff[k] = wrap1(COL * cy - (M - 1) + ls.g + 3 * k, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
-                            goff[3] = wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx);
-                            load_all();
+                                for (int k = 0; k < 3; ++k)
+                                    goff[k] = wrap1(COL * cy - (M - 1) + ls.g + 3 * k, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                                goff[3] = wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx);
+                                load_all();
+                            }
                         }
-                    }
-                    // hot loop (rotated: the next record is requested at the end of the body)
-                    PointRec A = load_rec(rec_w + p0 * REC_F, ls);
+                        // hot loop (rotated: the next record is requested at the end of the body)
+                        PointRec A = load_rec(rec_w + p0 * REC_F, ls);
 #pragma unroll 1
-                    for (int p = p0; p < p1; ++p) {
-                        const float wz[P] = {A.z0.x, A.z0.y, A.z0.z, A.z0.w, A.z1.x, A.z1.y, A.z1.z, A.z1.w, A.z2.x, A.z2.y, A.z2.z};
-                        u64 tk[4] = {0ull, 0ull, 0ull, 0ull};
+                        for (int p = p0; p < p1; ++p) {
+                            const float wz[P] = {A.z0.x, A.z0.y, A.z0.z, A.z0.w, A.z1.x, A.z1.y, A.z1.z, A.z1.w, A.z2.x, A.z2.y, A.z2.z};
+                            u64 tk[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-                        for (int i = 0; i < P; ++i) {
-                            const u64 wzz = pk2(wz[i], wz[i]);
+                            for (int i = 0; i < P; ++i) {
+                                const u64 wzz = pk2(wz[i], wz[i]);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][i], wzz, tk[k]);
+                                for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][i], wzz, tk[k]);
+                            }
+                            const u64 w01 = fmul2(pk2(A.wx, A.wx), pk2(A.wy.x, A.wy.y));
+                            const u64 w23 = fmul2(pk2(A.wx, A.wx3), pk2(A.wy.z, A.wy.w));
+                            const float2 wa = unpk2(w01), wb = unpk2(w23);
+                            u64 acc = fmul2(tk[0], pk2(wa.x, wa.x));
+                            acc = ffma2(tk[1], pk2(wa.y, wa.y), acc);
+                            acc = ffma2(tk[2], pk2(wb.x, wb.x), acc);
+                            acc = ffma2(tk[3], pk2(wb.y, wb.y), acc);
+                            part_w[(p - h0) * PART_LD + lane] = acc;
+                            A = load_rec(rec_w + min(p + 1, p1 - 1) * REC_F, ls);
                         }
-                        const u64 w01 = fmul2(pk2(A.wx, A.wx), pk2(A.wy.x, A.wy.y));
-                        const u64 w23 = fmul2(pk2(A.wx, A.wx3), pk2(A.wy.z, A.wy.w));
-                        const float2 wa = unpk2(w01), wb = unpk2(w23);
-                        u64 acc = fmul2(tk[0], pk2(wa.x, wa.x));
-                        acc = ffma2(tk[1], pk2(wa.y, wa.y), acc);
-                        acc = ffma2(tk[2], pk2(wb.x, wb.x), acc);
-                        acc = ffma2(tk[3], pk2(wb.y, wb.y), acc);
-                        part_w[p * PART_LD + lane] = acc;
-                        A = load_rec(rec_w + min(p + 1, p1 - 1) * REC_F, ls);
+                        p0 = p1;
                     }
-                    p0 = p1;
-                }
-                __syncwarp();
-                // ---- per batch: lanes 3p, 3p + 1, 3p + 2 add up the 32 lane partials of point p -------------------------
-                u64 sum = 0ull;
-                if (act) {
-                    const u64 *row = part_w + ep * PART_LD + ed;
+                    __syncwarp();
+                    // ---- lanes 2q, 2q + 1 add up the 32 lane partials of point h0 + q ---------------------------------------
+                    {
+                        const int q = lane >> 1, hh = lane & 1;
+                        u64 sum = 0ull;
+                        if (h0 + q < h1) {
+                            const u64 *row = part_w + q * PART_LD + hh;
 #pragma unroll
-                    for (int j = 0; j < 11; ++j)
-                        if (ed + 3 * j < 32) sum = rt::fadd2(sum, row[3 * j]);
+                            for (int j = 0; j < 16; ++j) sum = rt::fadd2(sum, row[2 * j]);
+                        }
+                        sum = rt::fadd2(sum, shfl_xor_u64(sum, 1));
+                        // lane h0 + q' stores point h0 + q': fetch its sum from lane 2 q'
+                        const u64 res = shfl_idx_u64(sum, (2 * (lane - h0)) & 31);
+                        if (lane >= h0 && lane < h1) {
+                            const float2 rv = unpk2(res);
+                            const float scale = prefactor * (nu_weights ? nu_weights[n_mine] : 1.f);
+                            vc[n_mine] = make_float2(rv.x * scale, rv.y * scale);
+                        }
+                    }
+                    __syncwarp();
                 }
-                sum = rt::fadd2(sum, rt::fadd2(shfl_down_u64(sum, 1), shfl_down_u64(sum, 2)));   // valid in lanes 3p
-                const u64 res = shfl_idx_u64(sum, min(3 * lane, 31));                               // lane p <- lane 3p
-                if (lane < nb) {
-                    const float2 rv = unpk2(res);
-                    const float scale = prefactor * (nu_weights ? nu_weights[n_out] : 1.f);
-                    vc[n_out] = make_float2(rv.x * scale, rv.y * scale);
-                }
-                __syncwarp();
             }
         }
     }
@@ -252,7 +240,7 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
 
 inline size_t interp_smem_bytes(int cs_stride)
 {
-    return spread_smem_bytes(cs_stride) + (size_t)NWARP * (BATCH * PART_LD + 16 * 32) * sizeof(u64);
+    return spread_smem_bytes(cs_stride) + (size_t)NWARP * (HALF * PART_LD + 16 * 32) * sizeof(u64);
 }
 
 }  // namespace cs

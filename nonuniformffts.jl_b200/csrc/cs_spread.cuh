@@ -13,8 +13,9 @@
 //               8 points at one point per 8 fine cells;
 //   new column / end of chunk   the whole window is added to the grid (44 reductions per lane) and restarts at zero.
 // Partial sums of different warps meet only in global memory (L2 reductions); the chunk order keeps the set of
-// concurrently active columns inside a slab of a few MB, so they meet in L2.  The kernel values are evaluated by 3 lanes
-// per point (one per dimension, batches of 10 points) into a warp-private record.  Shared memory holds only records and
+// concurrently active columns inside a slab of a few MB, so they meet in L2.  The kernel values are evaluated by one lane
+// per point (batches of 32 points) into a warp-private record; coordinates, permutation and values of the next batch arrive
+// through cp.async (no registers or scoreboards held across a batch).  Shared memory holds only records, staging and
 // the coefficient tables, so residency is bounded by registers (12 warps per SM).
 #pragma once
 #include "rt_common.cuh"
@@ -34,33 +35,24 @@ constexpr int M = 4, W = 8;
 constexpr int COL = 4;                    // column edge in x, y and layer thickness in z (cells)
 constexpr int SEG = 256;                  // z segment (cells): bins are 4 x 4 x SEG cells, SEG / 4 layers each
 constexpr int NWARP = 12;                 // warps per CTA (one CTA per SM): 168 registers per thread
-constexpr int BATCH = 10;                 // points per evaluation batch: 3 lanes per point
-constexpr int CHUNK = 240;                // points per work item
-constexpr int REC_F = 52;                 // floats per point record
+constexpr int BATCH = 32;                 // points per evaluation batch: one lane per point
+constexpr int CHUNK = 256;                // points per work item
+constexpr int REC_F = 52;                 // floats per point record (208 bytes: 16-byte stores of 8 lanes are conflict-free)
+constexpr int STAGE_F = 6 * 32;            // floats per warp of the global-load staging buffer: x, y, z, value (2), weight | index
 constexpr int OFF_WX = 0;                 // [0..11]  wx_pad[0..10], 0
 constexpr int OFF_HV = 12;                // [12..13] value (re, im) [spreading]
 constexpr int OFF_WY = rt::OFF_WY;        // [16..39] wyT rows (rt::store_y)
 constexpr int OFF_WZ = 40;                // [40..51] wz_pad[0..10], 0
 static_assert(OFF_WY == 16, "record layout shared with rt_common.cuh");
 
-// per-lane kernel parameters of ONE dimension (lane = 3 * point + dimension)
-__device__ __forceinline__ KernelParams<float> lane_kernel_params(const KernelParams<float> &kp, int d)
+// 2M = 8 kernel values of dimension D around x; the piecewise-polynomial fast path reads the coefficient rows as two
+// 16-byte vectors (same fmaf sequence as eval_kernel_values, bit-identical values).  Returns the 0-based cell.
+template <int D>
+__device__ __forceinline__ int eval_m4(const KernelParams<float> &kp, const float *cs, float x, float (&w)[W])
 {
-    KernelParams<float> kl = kp;
-    kl.N[0] = d == 0 ? kp.N[0] : (d == 1 ? kp.N[1] : kp.N[2]);
-    kl.beta[0] = d == 0 ? kp.beta[0] : (d == 1 ? kp.beta[1] : kp.beta[2]);
-    kl.tau[0] = d == 0 ? kp.tau[0] : (d == 1 ? kp.tau[1] : kp.tau[2]);
-    kl.dx[0] = d == 0 ? kp.dx[0] : (d == 1 ? kp.dx[1] : kp.dx[2]);
-    return kl;
-}
-
-// 2M = 8 kernel values of one dimension; the piecewise-polynomial fast path reads the coefficient rows as two 16-byte
-// vectors (same fmaf sequence as eval_kernel_values, bit-identical values)
-__device__ __forceinline__ int eval_m4(const KernelParams<float> &kl, const float *cs, float x, float (&w)[W])
-{
-    if (kl.mode == NUFFT_EVAL_FAST && kl.kind != NUFFT_KERNEL_BSPLINE && kl.kind != NUFFT_KERNEL_GAUSSIAN) {
+    if (kp.mode == NUFFT_EVAL_FAST && kp.kind != NUFFT_KERNEL_BSPLINE && kp.kind != NUFFT_KERNEL_GAUSSIAN) {
         float r;
-        const int i0 = point_to_cell0<float>(x, kl.N[0], r);
+        const int i0 = point_to_cell0<float>(x, kp.N[D], r);
         const float xt = 2.f * (r - (float)i0) - 1.f;
         const float4 *c4 = reinterpret_cast<const float4 *>(cs);
         float4 a = c4[2 * (M + 3)], b = c4[2 * (M + 3) + 1];
@@ -73,8 +65,34 @@ __device__ __forceinline__ int eval_m4(const KernelParams<float> &kl, const floa
         w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
         return i0;
     }
-    return eval_kernel_values<float, M>(kl, cs, 0, x, w);
+    return eval_kernel_values<float, M>(kp, cs, D, x, w);
 }
+
+// one lane evaluates the three 1-D kernels of its point into the point's record; returns the cells
+__device__ __forceinline__ void evaluate_point(const KernelParams<float> &kp, const float *cs_s, float x, float y, float z,
+                                               float *r, int &cx, int &cy, int &cz)
+{
+    float w[W], pw[P];
+    float4 *q;
+    cx = eval_m4<0>(kp, cs_s, x, w);
+    rt::pad_shift(w, cx & 3, pw);
+    q = reinterpret_cast<float4 *>(r + OFF_WX);
+    q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+    q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+    q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
+    cy = eval_m4<1>(kp, cs_s + kp.cs_stride, y, w);
+    rt::pad_shift(w, cy & 3, pw);
+    rt::store_y(r, pw);
+    cz = eval_m4<2>(kp, cs_s + 2 * kp.cs_stride, z, w);
+    rt::pad_shift(w, cz & 3, pw);
+    q = reinterpret_cast<float4 *>(r + OFF_WZ);
+    q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
+    q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
+    q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void red_cell(float2 *p, u64 v)
 {
@@ -127,21 +145,22 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH][REC_F]
-    float *cs_s = rec_all + NWARP * BATCH * REC_F;                           // [3][cs_stride]
+    float *stage_all = rec_all + NWARP * BATCH * REC_F;                      // [NWARP][STAGE_F]
+    float *cs_s = stage_all + NWARP * STAGE_F;                               // [3][cs_stride]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     float *rec_w = rec_all + warp * BATCH * REC_F;
+    // staging slots of this lane (global loads land here through cp.async: no registers, no scoreboards held across a batch)
+    float *st_x = stage_all + warp * STAGE_F + lane;                          // x, y, z at st_x[0], [32], [64]
+    float2 *st_v = reinterpret_cast<float2 *>(stage_all + warp * STAGE_F + 96) + lane;
+    float *st_w = stage_all + warp * STAGE_F + 160 + lane;                    // callback weight; reused for the index
+    int32_t *st_n = reinterpret_cast<int32_t *>(st_w);
 
     for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
     __syncthreads();                                   // the only CTA barrier: coefficient tables
 
     const rt::LaneSlots ls = rt::lane_slots(lane);
-    const int ep = lane / 3, ed = lane - 3 * ep;       // evaluation role: lane = 3 * point + dimension
-    const bool elane = lane < 3 * BATCH;
-    const float *xs_d = ed == 0 ? xs0 : (ed == 1 ? xs1 : xs2);
-    const KernelParams<float> kl = lane_kernel_params(kp, ed);
-    const float *cs_d = cs_s + ed * kp.cs_stride;
     const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
     const int plane = Nx * Ny;
 
@@ -197,66 +216,51 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
                 ++wl;
             };
 
-            // ---- software pipeline of the global loads: perm two batches ahead, coordinate / value one batch ahead --------
-            auto load_n = [&](int bi) -> int32_t {
-                const int k = k0 + bi * BATCH + ep;
-                return (elane && ed == 2 && k < k1) ? perm[k] : 0;
+            // ---- global loads: one lane per point, staged through cp.async one batch ahead (the index two steps ahead:
+            //      it is read back and used as the gather address of the value in the next step) --------------------------
+            auto issue_n = [&](int bi) {
+                const int k = k0 + bi * BATCH + lane;
+                if (k < k1) cp_async_cell<4>(st_n, perm + k);
             };
-            auto load_x = [&](int bi) -> float {
-                const int k = k0 + bi * BATCH + ep;
-                return (elane && k < k1) ? xs_d[k] : 0.f;
+            auto issue_xv = [&](int bi, int32_t n) {
+                const int k = k0 + bi * BATCH + lane;
+                if (k < k1) {
+                    cp_async_cell<4>(st_x, xs0 + k);
+                    cp_async_cell<4>(st_x + 32, xs1 + k);
+                    cp_async_cell<4>(st_x + 64, xs2 + k);
+                    cp_async_cell<8>(st_v, vc + n);
+                }
             };
-            auto load_v = [&](int bi, int32_t n) -> float2 {
-                const int k = k0 + bi * BATCH + ep;
-                return (elane && ed == 2 && k < k1) ? vc[n] : make_float2(0.f, 0.f);
-            };
-            auto load_w = [&](int bi, int32_t n) -> float {          // non-uniform callback weight (original index)
-                const int k = k0 + bi * BATCH + ep;
-                return (nu_weights && elane && ed == 2 && k < k1) ? nu_weights[n] : 1.f;
-            };
-            int32_t n1 = load_n(0);
-            float xq = load_x(0);
-            float2 vq = load_v(0, n1);
-            float wq = load_w(0, n1);
-            n1 = load_n(1);
+            issue_n(0);
+            cp_async_commit();
+            cp_async_wait0();
+            int32_t n_cur = *st_n;                         // original index of this lane's point of the batch being staged
+            float wgt = 1.f;
+            issue_xv(0, n_cur);
+            issue_n(1);
+            cp_async_commit();
 
             for (int bi = 0; bi < nbatches; ++bi) {
                 const int nb = min(BATCH, k1 - (k0 + bi * BATCH));
-                const float x = xq;
-                const float2 v = cmul(vq, wq);
-                const int32_t n2 = load_n(bi + 2);
-                xq = load_x(bi + 1);
-                vq = load_v(bi + 1, n1);
-                wq = load_w(bi + 1, n1);
-                n1 = n2;
+                cp_async_wait0();
+                const float x = st_x[0], y = st_x[32], z = st_x[64];
+                float2 v = *st_v;
+                if (nu_weights && lane < nb) wgt = nu_weights[n_cur];
+                n_cur = *st_n;
+                issue_xv(bi + 1, n_cur);
+                issue_n(bi + 2);
+                cp_async_commit();
 
-                // ---- evaluate: 3 lanes per point -----------------------------------------------------------------
-                const bool act = elane && ep < nb;
-                int cell = 0;
-                if (act) {
-                    float *r = rec_w + ep * REC_F;
-                    float w[W], pw[P];
-                    cell = eval_m4(kl, cs_d, x, w);
-                    rt::pad_shift(w, cell & 3, pw);
-                    if (ed == 1) {
-                        rt::store_y(r, pw);
-                    } else {
-                        float4 *q = reinterpret_cast<float4 *>(r + (ed == 0 ? OFF_WX : OFF_WZ));
-                        q[0] = make_float4(pw[0], pw[1], pw[2], pw[3]);
-                        q[1] = make_float4(pw[4], pw[5], pw[6], pw[7]);
-                        q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
-                    }
-                }
-                int mycol, mylay;                          // lane p < nb: column id and layer of point p of the batch
-                {
-                    const int src = min(3 * ep, 27);
-                    const int c0 = __shfl_sync(FULL, cell, src), c1 = __shfl_sync(FULL, cell, src + 1);
-                    const int col = ((c1 >> 2) << 16) | (c0 >> 2);
-                    if (act && ed == 2)
-                        *reinterpret_cast<float2 *>(rec_w + ep * REC_F + OFF_HV) = v;
-                    const int from = min(3 * lane + 2, 31);
-                    mycol = __shfl_sync(FULL, col, from);
-                    mylay = __shfl_sync(FULL, cell >> 2, from);
+                // ---- evaluate: one lane per point ----------------------------------------------------------------------
+                int mycol = -1, mylay = 0;                 // lane p < nb: column id and layer of point p of the batch
+                if (lane < nb) {
+                    float *r = rec_w + lane * REC_F;
+                    int cx, cy, cz;
+                    evaluate_point(kp, cs_s, x, y, z, r, cx, cy, cz);
+                    if (nu_weights) v = cmul(v, wgt);
+                    *reinterpret_cast<float2 *>(r + OFF_HV) = v;
+                    mycol = ((cy >> 2) << 16) | (cx >> 2);
+                    mylay = cz >> 2;
                 }
                 // runs of points sharing the window: bit p of `starts` is set when point p opens a new (column, layer)
                 unsigned starts;
@@ -306,7 +310,7 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
 
 inline size_t spread_smem_bytes(int cs_stride)
 {
-    return (size_t)NWARP * BATCH * REC_F * sizeof(float) + (size_t)(3 * cs_stride + 4) * sizeof(float) + 16;
+    return (size_t)NWARP * (BATCH * REC_F + STAGE_F) * sizeof(float) + (size_t)(3 * cs_stride + 4) * sizeof(float) + 16;
 }
 
 }  // namespace cs
