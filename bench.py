@@ -329,8 +329,9 @@ def run_ours(args):
         pass
     roof = {"bound": "hbm", "kernel": f"K-{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
-            "note": "K-spread is bound by shared-memory bandwidth (88% of the LSU wavefront peak in the ncu capture), "
-                    "not by HBM: see DESIGN.md section 3",
+            "note": "column-streaming kernels (cs_spread.cuh / cs_interp.cuh): not HBM-bound at one point per 8 fine cells — LSU "
+                    "wavefronts 66-72 %, FMA pipe 48-56 %, issue slots 59-67 % of peak in the ncu captures "
+                    "(profiles/r1_cs_*_ncu_details.txt); see DESIGN.md section 3",
             "launch_ms": dom_ms,
             "type1_incl_set_points_frac": (B_1 + B_sp) / (ms_t1 * 1e-3) / 1e9 / peak,
             "type2_incl_set_points_frac": (B_2 + B_sp) / (ms_t2 * 1e-3) / 1e9 / peak,

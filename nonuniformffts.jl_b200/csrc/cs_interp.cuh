@@ -50,7 +50,7 @@ __device__ __forceinline__ u64 ldg_cell(const float2 *p)
 
 template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
 __global__ void __launch_bounds__(32 * NWARP)
-cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__restrict__ perm, int32_t *work_counter,
+cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
                  const float *__restrict__ xs0, const float *__restrict__ xs1, const float *__restrict__ xs2, MutPtrPack vp, int C,
                  const float2 *__restrict__ us, int64_t ncells, float prefactor, const float *__restrict__ nu_weights)
 {
@@ -86,9 +86,9 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
         int item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1);
         item = __shfl_sync(FULL, item, 0);
-        const int64_t k0l = (int64_t)item * CHUNK;
+        const int64_t k0l = (int64_t)item * chunk;
         if (k0l >= np) break;
-        const int k0 = (int)k0l, k1 = min(k0 + CHUNK, np);
+        const int k0 = (int)k0l, k1 = min(k0 + chunk, np);
         const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
 
         for (int c = 0; c < C; ++c) {

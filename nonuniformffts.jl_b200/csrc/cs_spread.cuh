@@ -36,7 +36,12 @@ constexpr int COL = 4;                    // column edge in x, y and layer thick
 constexpr int SEG = 256;                  // z segment (cells): bins are 4 x 4 x SEG cells, SEG / 4 layers each
 constexpr int NWARP = 12;                 // warps per CTA (one CTA per SM): 168 registers per thread
 constexpr int BATCH = 32;                 // points per evaluation batch: one lane per point
-constexpr int CHUNK = 256;                // points per work item
+constexpr int CHUNK = 512;                // default points per work item (NUFFT_B200_CS_CHUNK overrides)
+inline int chunk_points()
+{
+    if (const char *e = getenv("NUFFT_B200_CS_CHUNK")) { const int v = atoi(e); if (v >= 32 && v <= (1 << 20)) return v / 32 * 32; }
+    return CHUNK;
+}
 constexpr int REC_F = 52;                 // floats per point record (208 bytes: 16-byte stores of 8 lanes are conflict-free)
 constexpr int STAGE_F = 6 * 32;            // floats per warp of the global-load staging buffer: x, y, z, value (2), weight | index
 constexpr int OFF_WX = 0;                 // [0..11]  wx_pad[0..10], 0
@@ -139,7 +144,7 @@ __device__ __forceinline__ void accumulate(u64 (&G)[4][P], const PointRec &q)
 
 template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
 __global__ void __launch_bounds__(32 * NWARP)       // (no min-blocks hint: with it ptxas renames the accumulators and adds ~30 MOVs per point)
-cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__restrict__ perm, int32_t *work_counter,
+cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
                  const float *__restrict__ xs0, const float *__restrict__ xs1, const float *__restrict__ xs2, PtrPack vp, int C,
                  float2 *__restrict__ us, int64_t ncells, const float *__restrict__ nu_weights)
 {
@@ -174,9 +179,9 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, const int32_t *__re
         int item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1);
         item = __shfl_sync(FULL, item, 0);
-        const int64_t k0l = (int64_t)item * CHUNK;
+        const int64_t k0l = (int64_t)item * chunk;
         if (k0l >= np) break;
-        const int k0 = (int)k0l, k1 = min(k0 + CHUNK, np);
+        const int k0 = (int)k0l, k1 = min(k0 + chunk, np);
         const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
 
         for (int c = 0; c < C; ++c) {

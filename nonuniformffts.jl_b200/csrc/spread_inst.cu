@@ -1,6 +1,7 @@
 // spread_inst.cu — instantiates the K-spread kernels for one (T, CPLX) pair.
 // Compiled four times: -DINST_T=float|double -DINST_CPLX=0|1 (keeps each nvcc job short).
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 #include "spread.cuh"
 #include "rt_spread.cuh"
@@ -39,7 +40,7 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
                 int nsm = 0;
                 CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
                 CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
-                kern<<<nsm, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, p.d_perm, p.d_counters, xs0, xs1, xs2, pack, cn, us,
+                kern<<<nsm, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters, xs0, xs1, xs2, pack, cn, us,
                                                         p.ncells, nuw);
                 NUFFT_COUNT_LAUNCH();
                 continue;
