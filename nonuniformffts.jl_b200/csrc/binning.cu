@@ -480,6 +480,12 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
         p.d_perm = res;
         p.sort_cur = (res == p.d_vals[0]) ? 0 : 1;
     }
+    // column-streaming plans (cs_spread.cuh / cs_interp.cuh) read the folded records through the permutation and pull
+    // fixed-size chunks of the sorted order: no sorted copy of the coordinates, no work-item table
+    if (p.geom.rt == 3) {
+        CUDA_TRY(cudaGetLastError());
+        return NUFFT_SUCCESS;
+    }
     if (np > 0) {
         gather_points_kernel<T><<<(unsigned)cdiv(np, 256), 256, 0, st>>>(
             p.D, p.opts.point_convention, p.x_stride, np, p.d_perm, (const T *)x[0], (const typename PointRec<T>::type *)p.d_rec,

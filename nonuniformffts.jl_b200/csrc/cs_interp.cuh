@@ -51,7 +51,7 @@ __device__ __forceinline__ u64 ldg_cell(const float2 *p)
 template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
 __global__ void __launch_bounds__(32 * NWARP)
 cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
-                 const float *__restrict__ xs0, const float *__restrict__ xs1, const float *__restrict__ xs2, MutPtrPack vp, int C,
+                 const float4 *__restrict__ prec, MutPtrPack vp, int C,
                  const float2 *__restrict__ us, int64_t ncells, float prefactor, const float *__restrict__ nu_weights)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -66,8 +66,8 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
     float *rec_w = rec_all + warp * BATCH * REC_F;
     u64 *part_w = part_all + warp * HALF * PART_LD;
     u64 *hst_w = hst_all + warp * 16 * 32 + lane;
-    float *st_x = stage_all + warp * STAGE_F + lane;                          // x, y, z at st_x[0], [32], [64]
-    int32_t *st_n = reinterpret_cast<int32_t *>(stage_all + warp * STAGE_F + 160) + lane;
+    float4 *st_x = reinterpret_cast<float4 *>(stage_all + warp * STAGE_F) + lane;      // folded (x, y, z, -) of the point
+    int32_t *st_n = reinterpret_cast<int32_t *>(stage_all + warp * STAGE_F + 192) + lane;
 
     for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
     __syncthreads();                                   // the only CTA barrier: coefficient tables
@@ -129,26 +129,34 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                 request_ahead();
             };
 
-            // ---- global loads: one lane per point, staged through cp.async one batch ahead --------------------------------
-            auto issue_x = [&](int bi) {
+            // ---- global loads: one lane per point, staged through cp.async: the index two steps ahead, the folded
+            //      coordinates (gathered through it from set_points' input-order records) one batch ahead ---------------------
+            auto issue_n = [&](int bi) {
                 const int k = k0 + bi * BATCH + lane;
-                if (k < k1) {
-                    cp_async_cell<4>(st_x, xs0 + k);
-                    cp_async_cell<4>(st_x + 32, xs1 + k);
-                    cp_async_cell<4>(st_x + 64, xs2 + k);
-                    cp_async_cell<4>(st_n, perm + k);
-                }
+                if (k < k1) cp_async_cell<4>(st_n, perm + k);
             };
-            issue_x(0);
+            auto issue_x = [&](int bi, int32_t n) {
+                const int k = k0 + bi * BATCH + lane;
+                if (k < k1) cp_async_cell<16>(st_x, prec + n);
+            };
+            issue_n(0);
+            cp_async_commit();
+            cp_async_wait0();
+            int32_t n_nxt = *st_n;                         // original index of this lane's point of the batch being staged
+            issue_x(0, n_nxt);
+            issue_n(1);
             cp_async_commit();
 
             for (int bi = 0; bi < nbatches; ++bi) {
                 const int kb = k0 + bi * BATCH;
                 const int nb = min(BATCH, k1 - kb);
                 cp_async_wait0();
-                const float x = st_x[0], y = st_x[32], z = st_x[64];
-                const int32_t n_mine = *st_n;              // original index of point `lane` of the batch
-                issue_x(bi + 1);
+                const float4 xyz = *st_x;
+                const float x = xyz.x, y = xyz.y, z = xyz.z;
+                const int32_t n_mine = n_nxt;              // original index of point `lane` of the batch
+                n_nxt = *st_n;
+                issue_x(bi + 1, n_nxt);
+                issue_n(bi + 2);
                 cp_async_commit();
 
                 // ---- evaluate: one lane per point ----------------------------------------------------------------------

@@ -14,7 +14,8 @@
 //   new column / end of chunk   the whole window is added to the grid (44 reductions per lane) and restarts at zero.
 // Partial sums of different warps meet only in global memory (L2 reductions); the chunk order keeps the set of
 // concurrently active columns inside a slab of a few MB, so they meet in L2.  The kernel values are evaluated by one lane
-// per point (batches of 32 points) into a warp-private record; coordinates, permutation and values of the next batch arrive
+// per point (batches of 32 points) into a warp-private record; permutation, folded coordinates (gathered through the
+// permutation from the input-order records set_points keeps: no sorted copy is made) and values of the next batch arrive
 // through cp.async (no registers or scoreboards held across a batch).  Shared memory holds only records, staging and
 // the coefficient tables, so residency is bounded by registers (12 warps per SM).
 #pragma once
@@ -43,7 +44,7 @@ inline int chunk_points()
     return CHUNK;
 }
 constexpr int REC_F = 52;                 // floats per point record (208 bytes: 16-byte stores of 8 lanes are conflict-free)
-constexpr int STAGE_F = 6 * 32;            // floats per warp of the global-load staging buffer: x, y, z, value (2), weight | index
+constexpr int STAGE_F = 7 * 32;            // floats per warp of the global-load staging buffer: (x, y, z, -) record, value (2), index
 constexpr int OFF_WX = 0;                 // [0..11]  wx_pad[0..10], 0
 constexpr int OFF_HV = 12;                // [12..13] value (re, im) [spreading]
 constexpr int OFF_WY = rt::OFF_WY;        // [16..39] wyT rows (rt::store_y)
@@ -145,7 +146,7 @@ __device__ __forceinline__ void accumulate(u64 (&G)[4][P], const PointRec &q)
 template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
 __global__ void __launch_bounds__(32 * NWARP)       // (no min-blocks hint: with it ptxas renames the accumulators and adds ~30 MOVs per point)
 cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
-                 const float *__restrict__ xs0, const float *__restrict__ xs1, const float *__restrict__ xs2, PtrPack vp, int C,
+                 const float4 *__restrict__ prec, PtrPack vp, int C,
                  float2 *__restrict__ us, int64_t ncells, const float *__restrict__ nu_weights)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -157,10 +158,9 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
     const unsigned FULL = 0xffffffffu;
     float *rec_w = rec_all + warp * BATCH * REC_F;
     // staging slots of this lane (global loads land here through cp.async: no registers, no scoreboards held across a batch)
-    float *st_x = stage_all + warp * STAGE_F + lane;                          // x, y, z at st_x[0], [32], [64]
-    float2 *st_v = reinterpret_cast<float2 *>(stage_all + warp * STAGE_F + 96) + lane;
-    float *st_w = stage_all + warp * STAGE_F + 160 + lane;                    // callback weight; reused for the index
-    int32_t *st_n = reinterpret_cast<int32_t *>(st_w);
+    float4 *st_x = reinterpret_cast<float4 *>(stage_all + warp * STAGE_F) + lane;      // folded (x, y, z, -) of the point
+    float2 *st_v = reinterpret_cast<float2 *>(stage_all + warp * STAGE_F + 128) + lane;
+    int32_t *st_n = reinterpret_cast<int32_t *>(stage_all + warp * STAGE_F + 192) + lane;
 
     for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
     __syncthreads();                                   // the only CTA barrier: coefficient tables
@@ -230,9 +230,7 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
             auto issue_xv = [&](int bi, int32_t n) {
                 const int k = k0 + bi * BATCH + lane;
                 if (k < k1) {
-                    cp_async_cell<4>(st_x, xs0 + k);
-                    cp_async_cell<4>(st_x + 32, xs1 + k);
-                    cp_async_cell<4>(st_x + 64, xs2 + k);
+                    cp_async_cell<16>(st_x, prec + n);       // set_points keeps the folded coordinates in input order
                     cp_async_cell<8>(st_v, vc + n);
                 }
             };
@@ -248,7 +246,8 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
             for (int bi = 0; bi < nbatches; ++bi) {
                 const int nb = min(BATCH, k1 - (k0 + bi * BATCH));
                 cp_async_wait0();
-                const float x = st_x[0], y = st_x[32], z = st_x[64];
+                const float4 xyz = *st_x;
+                const float x = xyz.x, y = xyz.y, z = xyz.z;
                 float2 v = *st_v;
                 if (nu_weights && lane < nb) wgt = nu_weights[n_cur];
                 n_cur = *st_n;

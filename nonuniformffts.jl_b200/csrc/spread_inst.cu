@@ -40,7 +40,7 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
                 int nsm = 0;
                 CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
                 CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
-                kern<<<nsm, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters, xs0, xs1, xs2, pack, cn, us,
+                kern<<<nsm, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters, (const float4 *)p.d_rec, pack, cn, us,
                                                         p.ncells, nuw);
                 NUFFT_COUNT_LAUNCH();
                 continue;
