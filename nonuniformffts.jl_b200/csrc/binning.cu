@@ -543,6 +543,11 @@ int binning_set_points(Plan &p, int64_t np, const void *const x[], int xstride)
         if (np > 0 && x[d] == nullptr) { set_error("null point array for dimension %d", d); return NUFFT_ERR_ARG; }
         p.user_x[d] = x[d];
     }
+    if (p.dual_geom) {
+        // column-streaming kernels when the register windows see enough points, shared-memory tiles otherwise
+        const int w = (p.cs_min_cells <= 0 || (double)np * p.cs_min_cells >= (double)p.ncells) ? 0 : 1;
+        p.geom = p.geom_alt[w]; p.nbins = p.nbins_alt[w]; p.key_bits = p.key_bits_alt[w];
+    }
     if (p.ev_ok) { cudaEventRecord(p.ev[0], p.stream); }
     int rc = p.f64 ? run_set_points<double>(p, np, x) : run_set_points<float>(p, np, x);
     if (rc != NUFFT_SUCCESS) return rc;

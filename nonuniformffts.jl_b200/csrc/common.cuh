@@ -175,6 +175,13 @@ struct Plan {
     TileGeom geom{};
     int64_t nbins = 1;
     int key_bits = 1;
+    // plans eligible for the column-streaming kernels keep BOTH geometries and pick per set_points by point density
+    // (cs below one point per cs_min_cells fine cells loses to the shared-memory tiles: windows see too few points)
+    bool dual_geom = false;
+    TileGeom geom_alt[2]{};          // [0] column-streaming, [1] shared-memory tiles
+    int64_t nbins_alt[2] = {1, 1};
+    int key_bits_alt[2] = {1, 1};
+    double cs_min_cells = 16.0;
     int64_t Np = -1;
     int64_t cap = 0;                 // capacity (points) of the buffers below
     const void *user_x[3] = {nullptr, nullptr, nullptr};

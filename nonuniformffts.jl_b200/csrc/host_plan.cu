@@ -242,7 +242,7 @@ static int padded_row(int Tx, int W, int cell_bytes)
     return best;
 }
 
-static bool choose_geometry(Plan &p)
+static bool choose_geometry(Plan &p, bool allow_cs = true)
 {
     TileGeom &g = p.geom;
     const int D = p.D, M = p.M, W = 2 * M;
@@ -280,7 +280,7 @@ static bool choose_geometry(Plan &p)
     // bins = columns of 4 x 4 cells in (x, y), segments of up to 256 cells in z; the sort key is refined by the layer
     // (4 cells in z) inside the segment, so the points of a column arrive bottom to top
     {
-        bool cs = D == 3 && M == 4 && !p.f64 && p.cplx && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
+        bool cs = allow_cs && D == 3 && M == 4 && !p.f64 && p.cplx && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
         if (const char *e = getenv("NUFFT_B200_CS")) cs = cs && atoi(e) != 0;
         for (int d = 0; d < D && cs; ++d)
             if (p.Nos[d] < 16 || p.Nos[d] > 65536 * 4) cs = false;
@@ -500,7 +500,18 @@ int host_plan_init(Plan &p)
     }
 
     // bins / tiles and method
-    const bool sm_ok = choose_geometry(p);
+    bool sm_ok = choose_geometry(p);
+    if (p.geom.rt == 3) {
+        // keep the tile geometry too: set_points picks by density (NUFFT_B200_CS_DENSITY = cells per point below which the
+        // column-streaming kernels are used; 0 = always)
+        p.geom_alt[0] = p.geom; p.nbins_alt[0] = p.nbins; p.key_bits_alt[0] = p.key_bits;
+        const bool tile_ok = choose_geometry(p, false);
+        p.geom_alt[1] = p.geom; p.nbins_alt[1] = p.nbins; p.key_bits_alt[1] = p.key_bits;
+        p.dual_geom = tile_ok;
+        if (const char *e = getenv("NUFFT_B200_CS_DENSITY")) p.cs_min_cells = atof(e);
+        p.geom = p.geom_alt[0]; p.nbins = p.nbins_alt[0]; p.key_bits = p.key_bits_alt[0];
+        sm_ok = true;
+    }
     if (o.gpu_method == NUFFT_METHOD_SHARED_MEMORY && !sm_ok) {
         set_error("GPU shared memory is too small for the chosen problem (element bytes %zu, M = %d, D = %d); "
                   "reduce some of these parameters or switch to gpu_method = global_memory",
@@ -561,8 +572,9 @@ int host_plan_init(Plan &p)
     }
 
     // binning tables that depend only on the plan
-    CUDA_TRY(cudaMalloc(&p.d_bin_offsets, (size_t)(p.nbins + 1) * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc(&p.d_item_start, (size_t)(p.nbins + 1) * sizeof(int32_t)));
+    const int64_t nbins_max = p.dual_geom ? std::max(p.nbins_alt[0], p.nbins_alt[1]) : p.nbins;
+    CUDA_TRY(cudaMalloc(&p.d_bin_offsets, (size_t)(nbins_max + 1) * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&p.d_item_start, (size_t)(nbins_max + 1) * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(&p.d_counters, 64 * sizeof(int32_t)));
     CUDA_TRY(cudaMemset(p.d_counters, 0, 64 * sizeof(int32_t)));
     if (o.record_timings) {

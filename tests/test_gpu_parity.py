@@ -216,6 +216,7 @@ def test_fast_path_kernel_families(nufft, oracle_mod, monkeypatch, family, case)
         monkeypatch.setenv(k, "0")
     if family != "tile":
         monkeypatch.setenv("NUFFT_B200_" + family.upper(), "1")
+    monkeypatch.setenv("NUFFT_B200_CS_DENSITY", "0")      # column-streaming at any density (default: >= 1 point per 16 cells)
     kw = dict(FAST_CASES[case])
     dims, Np = kw.pop("dims"), kw.pop("Np")
     run_case(nufft, oracle_mod, np.complex64, dims, Np, method="shared_memory", seed=3, **kw)
