@@ -109,6 +109,7 @@ template <typename T> struct KernelParams {
     const T *cs;     // device: per dim d a block of CS_STRIDE values:
                      //   [ (M+4)*2M polynomial coefs, layout [p][j] | M Gaussian exponentials ]
     int cs_stride;   // = (M+4)*2M + M
+    int i0_terms;    // Float64 Direct KB: terms of the I0 power series (kernel_eval.cuh), 0 = library cyl_bessel_i0
 };
 
 // ---- geometry of bins / tiles handed to spreading & interpolation kernels ---------------------
@@ -265,6 +266,21 @@ template <typename T> KernelParams<T> make_kernel_params(const Plan &p)
     }
     kp.cs = (const T *)p.d_cs;
     kp.cs_stride = p.cs_stride;
+    kp.i0_terms = 0;
+    if (sizeof(T) == 8 && p.opts.kernel == NUFFT_KERNEL_KAISER_BESSEL) {
+        double bmax = 0;
+        for (int d = 0; d < 3; ++d) bmax = p.kp_beta[d] > bmax ? p.kp_beta[d] : bmax;
+        const double q = 0.25 * bmax * bmax;
+        double term = 1, sum = 1;
+        int k = 0;
+        while (k < 200) {
+            ++k;
+            term *= q / ((double)k * (double)k);
+            sum += term;
+            if ((double)k * k > q && term < 1e-19 * sum) break;
+        }
+        kp.i0_terms = (k + 1 <= 64) ? k + 1 : 0;
+    }
     return kp;
 }
 
