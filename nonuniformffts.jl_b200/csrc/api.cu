@@ -183,7 +183,7 @@ int nufft_get_binning(nufft_plan h, const int32_t **perm, const int32_t **bin_of
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (p.Np < 0) { set_error("set_points has not been called"); return NUFFT_ERR_STATE; }
     if (perm) NUFFT_TRY(binning_coarse_perm(p, perm));     // rt plans: reference-order permutation rebuilt on demand
-    if (bin_offsets) *bin_offsets = p.d_bin_offsets;
+    if (bin_offsets) { NUFFT_TRY(binning_ensure_offsets(p)); *bin_offsets = p.d_bin_offsets; }
     if (nbins) *nbins = p.nbins;
     if (bin_dims) for (int d = 0; d < 3; ++d) bin_dims[d] = p.geom.B[d];
     return NUFFT_SUCCESS;

@@ -54,7 +54,7 @@ template <> struct PointRec<double> {
 };
 
 // ---- keys --------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool HIST>
 __global__ void __launch_bounds__(256)
 bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
                 uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count, typename PointRec<T>::type *__restrict__ rec)
@@ -94,13 +94,31 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
             // folded coordinates as one 16- / 32-byte record: the gather after the sort then touches one sector per point
             if (rec) rec[i] = PointRec<T>::make(f0, f1, f2);
         }
-        // warp-aggregated histogram: one atomic per distinct bin in the warp (clustered inputs)
-        const unsigned active = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned peers = __match_any_sync(active, key);
-            if (lane == __ffs(peers) - 1) atomicAdd(&bin_count[key + 1], (uint32_t)__popc(peers));
+        // warp-aggregated histogram: one atomic per distinct bin in the warp (clustered inputs).  Column-streaming plans
+        // (HIST = false) do not need bin offsets on the path: they are built on demand (binning_ensure_offsets)
+        if (HIST) {
+            const unsigned active = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned peers = __match_any_sync(active, key);
+                if (lane == __ffs(peers) - 1) atomicAdd(&bin_count[key + 1], (uint32_t)__popc(peers));
+            }
         }
     }
+}
+
+// bin histogram from the folded records (same cell arithmetic as bin_keys_kernel): introspection path of plans whose
+// set_points skips it
+__global__ void __launch_bounds__(256)
+bin_hist_from_rec_kernel(BinGeom g, int64_t np, const float4 *__restrict__ rec, uint32_t *__restrict__ bin_count)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    const float4 r = rec[i];
+    float t;
+    const int b0 = point_to_cell0<float>(r.x, g.N[0], t) / g.B[0];
+    const int b1 = point_to_cell0<float>(r.y, g.N[1], t) / g.B[1];
+    const int b2 = point_to_cell0<float>(r.z, g.N[2], t) / g.B[2];
+    atomicAdd(&bin_count[(b2 * g.nb[1] + b1) * g.nb[0] + b0 + 1], 1u);
 }
 
 // ---- exclusive scan (uint32, in place), three kernels -------------------------------------------
@@ -410,11 +428,14 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     cudaStream_t st = p.stream;
 
     uint32_t *bin_count = (uint32_t *)p.d_bin_offsets;
-    CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
+    const bool hist = g.rt != 3;            // column-streaming plans: offsets on demand
+    p.offsets_valid = hist;
+    if (hist) CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
     if (np > 0) {
         const int grid = (int)std::min<int64_t>(cdiv(np, 256), 148 * 16);
-        bin_keys_kernel<T><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count,
-                                                 p.D > 1 ? (typename PointRec<T>::type *)p.d_rec : nullptr);
+        auto *rec = p.D > 1 ? (typename PointRec<T>::type *)p.d_rec : nullptr;
+        if (hist) bin_keys_kernel<T, true><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec);
+        else bin_keys_kernel<T, false><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec);
         NUFFT_COUNT_LAUNCH();
     }
     // slot b+1 holds the count of bin b and slot 0 stays 0: an inclusive scan of this array is exactly
@@ -463,7 +484,7 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
     NUFFT_TRY(set_points_impl<T>(p, np, x));
     cudaStream_t st = p.stream;
     const int64_t nb1 = p.nbins + 1;
-    NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_bin_offsets, nb1, true));
+    if (p.offsets_valid) NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_bin_offsets, nb1, true));
     p.perm_coarse_ptr = nullptr;
 
     // stable LSD radix sort of (key, index)
@@ -512,8 +533,29 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
 // rt plans order the points by (bin, sub-bin); the reference-order permutation (stable by bin only, what
 // BlockDataGPU.pointperm holds after the 1-thread counting sort, src/blocking/cpu.jl:73-111) is rebuilt on demand:
 // bin of every ORIGINAL index (scatter through the fine permutation), then the same stable radix sort on the bin bits.
+// bin offsets (cumulative_npoints_per_block) of plans whose set_points does not build them (column-streaming)
+int binning_ensure_offsets(Plan &p)
+{
+    if (p.offsets_valid) return NUFFT_SUCCESS;
+    const TileGeom &g = p.geom;
+    BinGeom bg{};
+    bg.D = p.D;
+    for (int d = 0; d < 3; ++d) { bg.N[d] = g.N[d]; bg.B[d] = g.B[d]; bg.nb[d] = g.nb[d]; }
+    uint32_t *bin_count = (uint32_t *)p.d_bin_offsets;
+    CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), p.stream));
+    if (p.Np > 0) {
+        bin_hist_from_rec_kernel<<<(unsigned)cdiv(p.Np, 256), 256, 0, p.stream>>>(bg, p.Np, (const float4 *)p.d_rec, bin_count);
+        NUFFT_COUNT_LAUNCH();
+    }
+    NUFFT_TRY(scan_u32(p, bin_count, p.nbins + 1, true));
+    CUDA_TRY(cudaGetLastError());
+    p.offsets_valid = true;
+    return NUFFT_SUCCESS;
+}
+
 int binning_coarse_perm(Plan &p, const int32_t **perm)
 {
+    NUFFT_TRY(binning_ensure_offsets(p));
     if (p.geom.nsub <= 1 || p.Np <= 0 || p.nbins <= 1) { *perm = p.d_perm; return NUFFT_SUCCESS; }
     if (p.perm_coarse_ptr) { *perm = p.perm_coarse_ptr; return NUFFT_SUCCESS; }
     const int64_t np = p.Np;

@@ -193,6 +193,7 @@ struct Plan {
     void *d_xs[3] = {nullptr, nullptr, nullptr};       // sorted, folded coordinates (T)
     void *d_rec = nullptr;                             // folded coordinates in input order, one 4 x T record per point (D > 1)
     int32_t *d_bin_offsets = nullptr;                  // nbins + 1
+    bool offsets_valid = true;                         // false: build on demand (binning_ensure_offsets)
     int32_t *d_perm_coarse = nullptr;                  // rt plans: bin-stable permutation, built on demand (introspection)
     int64_t perm_coarse_cap = 0;
     const int32_t *perm_coarse_ptr = nullptr;          // valid result of the last on-demand build (reset by set_points)
@@ -250,6 +251,7 @@ int pfft_type2_run(Plan &p, const void *const uhat[], const nufft_callbacks *cb)
 int fft_forward(Plan &p);
 int fft_backward(Plan &p);
 int scan_u32(Plan &p, uint32_t *data, int64_t n, bool inclusive);          // binning.cu (in place prefix sum)
+int binning_ensure_offsets(Plan &p);                                       // binning.cu (column-streaming plans: on demand)
 int binning_coarse_perm(Plan &p, const int32_t **perm);                    // binning.cu (rt plans: reference-order permutation)
 
 template <typename T> KernelParams<T> make_kernel_params(const Plan &p)

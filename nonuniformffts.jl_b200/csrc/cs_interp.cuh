@@ -75,6 +75,7 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
     const rt::LaneSlots ls = rt::lane_slots(lane);
     const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
     const int plane = Nx * Ny;
+    const unsigned long long pol = l2_evict_first_policy();
 
     u64 G[4][P];                                       // window: planes COL * wl - 3 .. COL * wl + 7
 #pragma unroll
@@ -133,11 +134,11 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
             //      coordinates (gathered through it from set_points' input-order records) one batch ahead ---------------------
             auto issue_n = [&](int bi) {
                 const int k = k0 + bi * BATCH + lane;
-                if (k < k1) cp_async_cell<4>(st_n, perm + k);
+                if (k < k1) cp_async_stream<4>(st_n, perm + k, pol);
             };
             auto issue_x = [&](int bi, int32_t n) {
                 const int k = k0 + bi * BATCH + lane;
-                if (k < k1) cp_async_cell<16>(st_x, prec + n);
+                if (k < k1) cp_async_stream<16>(st_x, prec + n, pol);
             };
             issue_n(0);
             cp_async_commit();
@@ -236,7 +237,7 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                         if (lane >= h0 && lane < h1) {
                             const float2 rv = unpk2(res);
                             const float scale = prefactor * (nu_weights ? nu_weights[n_mine] : 1.f);
-                            vc[n_mine] = make_float2(rv.x * scale, rv.y * scale);
+                            __stcs(vc + n_mine, make_float2(rv.x * scale, rv.y * scale));     // streaming store: written once
                         }
                     }
                     __syncwarp();

@@ -97,6 +97,24 @@ __device__ __forceinline__ void evaluate_point(const KernelParams<float> &kp, co
     q[2] = make_float4(pw[8], pw[9], pw[10], 0.f);
 }
 
+// streamed / gathered operands (permutation, point records, values) are used once: fetch them with an evict-first L2
+// policy so that they do not displace the grid lines that the reductions (spreading) and window loads (interpolation) reuse
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <int BYTES> __device__ __forceinline__ void cp_async_stream(void *smem, const void *gmem, unsigned long long pol)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -168,6 +186,7 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
     const rt::LaneSlots ls = rt::lane_slots(lane);
     const int Nx = g.N[0], Ny = g.N[1], Nz = g.N[2];
     const int plane = Nx * Ny;
+    const unsigned long long pol = l2_evict_first_policy();
 
     u64 G[4][P];
 #pragma unroll
@@ -225,13 +244,13 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
             //      it is read back and used as the gather address of the value in the next step) --------------------------
             auto issue_n = [&](int bi) {
                 const int k = k0 + bi * BATCH + lane;
-                if (k < k1) cp_async_cell<4>(st_n, perm + k);
+                if (k < k1) cp_async_stream<4>(st_n, perm + k, pol);
             };
             auto issue_xv = [&](int bi, int32_t n) {
                 const int k = k0 + bi * BATCH + lane;
                 if (k < k1) {
-                    cp_async_cell<16>(st_x, prec + n);       // set_points keeps the folded coordinates in input order
-                    cp_async_cell<8>(st_v, vc + n);
+                    cp_async_stream<16>(st_x, prec + n, pol);   // set_points keeps the folded coordinates in input order
+                    cp_async_stream<8>(st_v, vc + n, pol);
                 }
             };
             issue_n(0);
