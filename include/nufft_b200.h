@@ -127,9 +127,10 @@ int  nufft_set_points_matrix(nufft_plan plan, int64_t np, const void *xmat);
 int  nufft_get_binning(nufft_plan plan, const int32_t **perm, const int32_t **bin_offsets,
                        int64_t *nbins, int64_t bin_dims[3]);
 
-/* The order the kernels actually use.  Plans on the register-tile fast path (3-D, Float32, HalfSupport(4)) refine every
- * bin into sub-bins of 4x4x4 cells and sort by key = bin * nsub + ((sy * sub_dims[0] + sx) * sub_dims[2] + sz) (stable),
- * a refinement of the reference order; nufft_get_binning then rebuilds the bin-stable permutation on demand.
+/* The order the kernels actually use.  Plans on the column-streaming fast path (3-D, ComplexF32, HalfSupport(4), at least
+ * one point per 16 fine cells) use bins of 4 x 4 x Bz cells refined into layers of 4 cells along z and sort by
+ * key = bin * nsub + layer (stable), a refinement of the reference order; nufft_get_binning then rebuilds the bin-stable
+ * permutation (and the bin offsets) on demand.
  * Other plans: nsub = 1 and both getters agree.  fine_offsets has nfine + 1 entries. */
 int  nufft_get_binning_fine(nufft_plan plan, const int32_t **perm, const int32_t **fine_offsets,
                             int64_t *nfine, int64_t sub_dims[3]);

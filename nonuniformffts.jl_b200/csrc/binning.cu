@@ -71,7 +71,7 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
             int c = point_to_cell0<T>(f0, g.N[0], r);
             int b = c / g.B[0];
             uint32_t k = (uint32_t)b;
-            int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // rt: 4-cell columns in x, y; single cells in z
+            int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // refined plans: sub-bins of 4 cells
             if (g.D > 1) {
                 f1 = fold_point<T>(x1[i * g.xstride], g.convention);
                 c = point_to_cell0<T>(f1, g.N[1], r);
@@ -84,11 +84,11 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
                 c = point_to_cell0<T>(f2, g.N[2], r);
                 b = c / g.B[2];
                 sz = c - b * g.B[2];
-                if (g.rt >= 2) sz >>= 2;                       // wp / cs: sub-bins (layers) of 4 cells in z
+                sz >>= 2;                                      // layers of 4 cells in z
                 k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
             }
-            // rt plans: refine by (column, z cell) so that the points of a 4x4-cell column are contiguous and
-            // ordered along z; the histogram stays per bin
+            // column-streaming plans: refine by the layer inside the bin (a column of 4 x 4 cells) so that the points of a
+            // column are contiguous and ordered along z; the histogram stays per bin
             key = k;
             keys[i] = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
             // folded coordinates as one 16- / 32-byte record: the gather after the sort then touches one sector per point

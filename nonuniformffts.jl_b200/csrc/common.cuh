@@ -123,10 +123,9 @@ struct TileGeom {
     int tile_cells;  // allocated cells per tile
     int chunk;       // max points per work item
     int batch;       // points per evaluation batch (shared-memory staging)
-    // register-window fast path (rt_spread.cuh / rt_interp.cuh; D = 3, M = 4, Float32): bins are refined into
-    // columns of 4 x 4 cells and single cells along z; the sort key is bin * nsub + ((cy * sub[0] + cx) * sub[2] + cz)
-    int rt;          // 1: register-window kernels (rt_*.cuh); 2: warp-private-tile kernels (wp_*.cuh: bins 8^3, sub-bins 4^3);
-                     // 3: column-streaming kernels (cs_*.cuh: bins 4 x 4 x 64, layers of 4 cells)
+    // column-streaming fast path (cs_spread.cuh / cs_interp.cuh; D = 3, M = 4, ComplexF32): bins of 4 x 4 x Bz cells are
+    // refined into layers of 4 cells along z; the sort key is bin * nsub + layer
+    int rt;          // 3 when the plan is on that path (0 otherwise)
     int sub[3];      // sub-bins per bin along each dimension (1 when !rt)
     int nsub;        // sub[0] * sub[1] * sub[2]
 };
@@ -194,7 +193,7 @@ struct Plan {
     void *d_rec = nullptr;                             // folded coordinates in input order, one 4 x T record per point (D > 1)
     int32_t *d_bin_offsets = nullptr;                  // nbins + 1
     bool offsets_valid = true;                         // false: build on demand (binning_ensure_offsets)
-    int32_t *d_perm_coarse = nullptr;                  // rt plans: bin-stable permutation, built on demand (introspection)
+    int32_t *d_perm_coarse = nullptr;                  // refined plans: bin-stable permutation, built on demand (introspection)
     int64_t perm_coarse_cap = 0;
     const int32_t *perm_coarse_ptr = nullptr;          // valid result of the last on-demand build (reset by set_points)
     int sort_cur = 0;                                  // which of d_vals[] holds the permutation
@@ -224,13 +223,6 @@ static inline int record_size(int D, int M)
     return D == 1 ? wslot : (D == 2 ? 2 * wslot : 2 * wslot + yslot);
 }
 
-// floats per point record of the register-tile kernels (rt_common.cuh)
-// warp-private-tile kernels are the default for their configuration class (NUFFT_B200_WP=0 disables)
-#ifndef NUFFT_WP_DEFAULT
-#define NUFFT_WP_DEFAULT 0
-#endif
-constexpr int RT_REC_F = 52;
-constexpr int RT_SREC_F = 60;      // spreading records carry value x wz (complex): rt_spread.cuh
 
 // kernel-launch helper: ceil-div
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -19,7 +19,7 @@
 // through cp.async (no registers or scoreboards held across a batch).  Shared memory holds only records, staging and
 // the coefficient tables, so residency is bounded by registers (12 warps per SM).
 #pragma once
-#include "rt_common.cuh"
+#include "window_common.cuh"
 #include "spread.cuh"
 
 namespace nufft {
@@ -49,7 +49,7 @@ constexpr int OFF_WX = 0;                 // [0..11]  wx_pad[0..10], 0
 constexpr int OFF_HV = 12;                // [12..13] value (re, im) [spreading]
 constexpr int OFF_WY = rt::OFF_WY;        // [16..39] wyT rows (rt::store_y)
 constexpr int OFF_WZ = 40;                // [40..51] wz_pad[0..10], 0
-static_assert(OFF_WY == 16, "record layout shared with rt_common.cuh");
+static_assert(OFF_WY == 16, "record layout shared with window_common.cuh");
 
 // 2M = 8 kernel values of dimension D around x; the piecewise-polynomial fast path reads the coefficient rows as two
 // 16-byte vectors (same fmaf sequence as eval_kernel_values, bit-identical values).  Returns the 0-based cell.

@@ -305,78 +305,6 @@ static bool choose_geometry(Plan &p, bool allow_cs = true)
         }
     }
 
-    // ---- warp-private-tile fast path (wp_spread.cuh / wp_interp.cuh): D = 3, M = 4, ComplexF32 --------------------
-    // bins of 8 x 8 x 8 cells = 2 x 2 x 2 sub-bins of 4 x 4 x 4 cells; the sort key is refined by the sub-bin
-    {
-        bool wp = D == 3 && M == 4 && !p.f64 && p.cplx && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
-        if (const char *e = getenv("NUFFT_B200_WP")) wp = wp && atoi(e) != 0;
-        else wp = wp && NUFFT_WP_DEFAULT;
-        for (int d = 0; d < D && wp; ++d)
-            if (p.Nos[d] < 16 || (p.Nos[d] & 1)) wp = false;
-        if (wp) {
-            g.rt = 2;
-            int Bw[3] = {8, 8, 8};
-            tile_bytes(Bw, T, S);               // strides of the generic shared-memory kernels (fallbacks)
-            int64_t nbins = 1;
-            for (int d = 0; d < 3; ++d) {
-                g.B[d] = 8; g.T[d] = T[d]; g.S[d] = S[d];
-                g.sub[d] = 2;
-                g.nb[d] = (int)cdiv(p.Nos[d], 8);
-                nbins *= g.nb[d];
-            }
-            g.nsub = 8;
-            g.tile_cells = S[0] * T[1] * T[2];
-            p.nbins = nbins;
-            p.key_bits = 1;
-            while (((int64_t)1 << p.key_bits) < nbins * g.nsub) ++p.key_bits;
-            return true;
-        }
-    }
-
-    // ---- register-window fast path (rt_spread.cuh / rt_interp.cuh): D = 3, M = 4, Float32 ----------------------
-    // bins of 16 x 16 cells in (x, y) (4 x 4 columns of 4 x 4 cells) and Bz cells along z, Bz chosen so that two CTAs
-    // (tile + point records) are resident per SM; the sort key is refined by (column, z cell)
-    {
-        bool rt = D == 3 && M == 4 && !p.f64 && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
-        {   // opt-in until it beats the shared-memory-tile kernels (NUFFT_B200_RT=1)
-            const char *e = getenv("NUFFT_B200_RT");
-            rt = rt && e && atoi(e) != 0;
-        }
-        int Br[3] = {16, 16, 12};
-        if (const char *e = getenv("NUFFT_B200_RT_BZ")) { const int v = atoi(e); if (v >= 1 && v <= 64) Br[2] = v; }
-        for (int d = 0; d < D && rt; ++d) {
-            if (d < 2 && bcap(d) < 16) rt = false;
-            Br[d] = (int)std::min<int64_t>(Br[d], bcap(d));
-        }
-        auto rt_need = [&](int bz) -> size_t {
-            const size_t tile = (size_t)(16 + W - 1) * (16 + W - 1) * (bz + W - 1) * cell_bytes;
-            return tile + (size_t)4 * 32 * RT_SREC_F * sizeof(float) + ((size_t)D * p.cs_stride + 4) * p.real_bytes + 256;
-        };
-        if (rt) {
-            while (Br[2] > 4 && rt_need(Br[2]) > (size_t)(SMEM_PER_SM / 2 - 1024)) --Br[2];
-            if (rt_need(Br[2]) > (size_t)SMEM_MAX_CTA) rt = false;
-        }
-        if (rt) {
-            g.rt = 1;
-            g.batch = 32;
-            int64_t nbins = 1;
-            for (int d = 0; d < 3; ++d) {
-                g.B[d] = Br[d]; g.T[d] = Br[d] + W - 1;
-                g.sub[d] = d < 2 ? Br[d] / 4 : Br[d];
-                g.nb[d] = (int)cdiv(p.Nos[d], Br[d]);
-                nbins *= g.nb[d];
-            }
-            g.nsub = g.sub[0] * g.sub[1] * g.sub[2];
-            g.S[0] = g.T[0];
-            g.S[1] = g.S[0];
-            g.S[2] = g.S[0] * g.T[1];
-            g.tile_cells = g.S[0] * g.T[1] * g.T[2];
-            p.nbins = nbins;
-            p.key_bits = 1;
-            while (((int64_t)1 << p.key_bits) < nbins * g.nsub) ++p.key_bits;
-            return true;
-        }
-    }
     if (user) {
         for (int d = 0; d < D; ++d) {
             int64_t b = p.opts.block_dims[d] > 0 ? p.opts.block_dims[d] : 16;

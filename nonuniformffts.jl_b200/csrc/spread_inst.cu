@@ -4,8 +4,6 @@
 #include <cstdlib>
 #include <type_traits>
 #include "spread.cuh"
-#include "rt_spread.cuh"
-#include "wp_spread.cuh"
 #include "cs_spread.cuh"
 
 #ifndef INST_T
@@ -42,36 +40,6 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
                 CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
                 kern<<<nsm, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters, (const float4 *)p.d_rec, pack, cn, us,
                                                         p.ncells, nuw);
-                NUFFT_COUNT_LAUNCH();
-                continue;
-            }
-            if (p.geom.rt == 2 && p.method == NUFFT_METHOD_SHARED_MEMORY) {
-                auto kern = wp::wp_spread_kernel<void>;
-                const size_t smem = wp::spread_smem_bytes(p.cs_stride);
-                const int nthreads = 32 * wp::NWARP;
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int nsm = 0;
-                CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
-                SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
-                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
-                kern<<<nsm, nthreads, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, nuw);
-                NUFFT_COUNT_LAUNCH();
-                continue;
-            }
-        }
-        if constexpr (std::is_same<T, float>::value && D == 3 && M == 4) {
-            if (p.geom.rt == 1 && p.method == NUFFT_METHOD_SHARED_MEMORY) {
-                auto kern = rt::rt_spread_kernel<CPLX>;
-                const size_t smem = rt::spread_smem_bytes(p.geom, p.cs_stride, sizeof(Cell));
-                const int nthreads = 32 * rt::SPREAD_NWARP;
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int occ = 0, nsm = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem));
-                CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
-                if (occ < 1) { set_error("rt_spread_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
-                SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
-                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
-                kern<<<nsm * occ, nthreads, smem, st>>>(kp, p.geom, a, xs0, xs1, xs2, pack, cn, us, p.ncells, nuw);
                 NUFFT_COUNT_LAUNCH();
                 continue;
             }

@@ -439,9 +439,9 @@ class PlanNUFFT:
         return p, o, tuple(int(bd[d]) for d in range(self._ndims))
 
     def binning_fine(self):
-        """(perm, fine_offsets, sub_dims): the (bin, sub-bin) order the kernels use.  Plans on the register-window
-        fast path refine every bin into sub_dims sub-bins (4 x 4-cell columns, single cells along z) and do not
-        materialise sub-bin offsets (fine_offsets is None); other plans: identical to `binning()`, sub_dims (1, 1, 1)."""
+        """(perm, fine_offsets, sub_dims): the (bin, sub-bin) order the kernels use.  Column-streaming plans refine every
+        bin (a column of 4 x 4 cells, up to 256 cells along z) into sub_dims layers of 4 cells and do not materialise
+        sub-bin offsets (fine_offsets is None); other plans: identical to `binning()`, sub_dims (1, 1, 1)."""
         perm, off = C.c_void_p(), C.c_void_p()
         nf = C.c_int64()
         sd = (C.c_int64 * 3)()

@@ -64,10 +64,7 @@ def _rel(a, b, torch):
 @pytest.mark.parametrize("family", ["cs", "tile"])
 def test_c3_full_size_properties(nufft, oracle_mod, monkeypatch, family):
     import torch
-    for k in ("NUFFT_B200_CS", "NUFFT_B200_WP", "NUFFT_B200_RT"):
-        monkeypatch.setenv(k, "0")
-    if family == "cs":
-        monkeypatch.setenv("NUFFT_B200_CS", "1")
+    monkeypatch.setenv("NUFFT_B200_CS", "1" if family == "cs" else "0")
     xs, v, u = _inputs(torch)
     ref1, ref2 = _oracle_results(oracle_mod, xs, v, u, 3)
     ref1, ref2 = torch.from_numpy(ref1).cuda(), torch.from_numpy(ref2).cuda()
@@ -148,10 +145,7 @@ def test_c3_kernel_families_agree(nufft, monkeypatch):
     xs, v, u = _inputs(torch, seed=9)
     res = {}
     for family in ("cs", "tile"):
-        for k in ("NUFFT_B200_CS", "NUFFT_B200_WP", "NUFFT_B200_RT"):
-            monkeypatch.setenv(k, "0")
-        if family == "cs":
-            monkeypatch.setenv("NUFFT_B200_CS", "1")
+        monkeypatch.setenv("NUFFT_B200_CS", "1" if family == "cs" else "0")
         plan = _plan(nufft, torch)
         plan.set_points(tuple(xs))
         o1 = torch.empty((N, N, N), dtype=torch.complex64, device="cuda")

@@ -39,13 +39,13 @@ def run_case(nufft, oracle_mod, dtype, dims, Np, *, m=4, sigma=2.0, kernel="back
     _, cum_o, perm_o = op.sort_points(xs, bdims)
     assert np.array_equal(off.cpu().numpy(), cum_o), "bin offsets differ from the oracle"
     assert np.array_equal(perm.cpu().numpy(), perm_o), "permutation differs from the oracle (stable order)"
-    # the order the kernels use: plans on the warp-private-tile / register-window fast paths refine the bins into
-    # sub-bins of 4 x 4 x 4 / 4 x 4 x 1 cells; expected = stable sort by (bin, sub-bin) of the oracle's own cell indices
+    # the order the kernels use: column-streaming plans refine the bins (columns of 4 x 4 cells, up to 256 cells along z)
+    # into layers of 4 cells; expected = stable sort by (bin, layer) of the oracle's own cell indices
     fperm, foff, sub = gp.binning_fine()
     if sub != (1, 1, 1):
         assert D == 3 and all(bdims[d] % sub[d] == 0 for d in range(3))
-        sw = [bdims[d] // sub[d] for d in range(3)]        # sub-bin edge: (4, 4, 1) register-window, (4, 4, 4) warp-private
-        assert sw in ([4, 4, 1], [4, 4, 4])
+        sw = [bdims[d] // sub[d] for d in range(3)]        # sub-bin edge
+        assert sw == [4, 4, 4]
         cell, _, _ = op.sort_points(xs, (1, 1, 1))
         cell = cell.astype(np.int64)
         c = [cell % op.Nos[0], (cell // op.Nos[0]) % op.Nos[1], cell // (op.Nos[0] * op.Nos[1])]
@@ -206,16 +206,13 @@ FAST_CASES = [
 ]
 
 
-@pytest.mark.parametrize("family", ["cs", "wp", "rt", "tile"])
+@pytest.mark.parametrize("family", ["cs", "tile"])
 @pytest.mark.parametrize("case", range(len(FAST_CASES)))
 def test_fast_path_kernel_families(nufft, oracle_mod, monkeypatch, family, case):
-    """3-D, HalfSupport(4), ComplexF32: every kernel family that serves the headline configuration class — column-streaming
-    (default), warp-private tiles, register windows (both opt-in) and the generic shared-memory tiles — against the oracle,
-    including the refined sort order each of them asks set_points for."""
-    for k in ("NUFFT_B200_CS", "NUFFT_B200_WP", "NUFFT_B200_RT"):
-        monkeypatch.setenv(k, "0")
-    if family != "tile":
-        monkeypatch.setenv("NUFFT_B200_" + family.upper(), "1")
+    """3-D, HalfSupport(4), ComplexF32: both kernel families that serve the headline configuration class — column-streaming
+    (default from one point per 16 fine cells) and the generic shared-memory tiles — against the oracle, including the
+    refined sort order the column-streaming kernels ask set_points for."""
+    monkeypatch.setenv("NUFFT_B200_CS", "1" if family == "cs" else "0")
     monkeypatch.setenv("NUFFT_B200_CS_DENSITY", "0")      # column-streaming at any density (default: >= 1 point per 16 cells)
     kw = dict(FAST_CASES[case])
     dims, Np = kw.pop("dims"), kw.pop("Np")

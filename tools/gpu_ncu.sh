@@ -1,6 +1,6 @@
 # ncu --set full capture of one kernel (regex $1) of the C3 workload; keeps CSV/text pages (the .ncu-rep only if small)
 set -x
-K=${1:-rt_spread}
+K=${1:-cs_spread}
 TAG=${2:-$K}
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s ${3:-1} -c 1 -f -o /tmp/$TAG python tools/run_c3.py --iters 2 > gpurun_out/ncu_$TAG.log 2>&1
 ncu -i /tmp/$TAG.ncu-rep --page details > gpurun_out/${TAG}_details.txt 2>&1
