@@ -99,6 +99,13 @@ typedef struct {
     const void *nu_weights;          /* T[Np] device: v[c] *= w[n], n = ORIGINAL point index           */
     const void *const *u_factor_sep; /* D device tables of T, len size(p)[d]: w[c] *= prod_d f_d[i_d]  */
     const void *u_factor_dense;      /* T array of dims size(p): w[c] *= f[I]                           */
+    /* general callbacks (optional; read only when struct_size covers them): CUDA C++ source compiled with NVRTC once per
+     * plan, defining nufft_cb_nonuniform(nufft_cell (&v)[NUFFT_C], long long n, const void *user) after
+     * `#define NUFFT_HAS_NONUNIFORM 1` and / or nufft_cb_uniform(nufft_cplx (&w)[NUFFT_C], const int (&idx)[3],
+     * const void *user) after `#define NUFFT_HAS_UNIFORM 1` — the arbitrary closures of src/plan.jl:146-164; applied
+     * where the reference applies them (csrc/callbacks_jit.cu), in addition to the menu above. */
+    const char *nvrtc_src;
+    const void *user_data;           /* device pointer handed to the callbacks                          */
 } nufft_callbacks;
 
 /* ---- plan lifetime: PlanNUFFT constructors, src/plan.jl:467-599 ---- */

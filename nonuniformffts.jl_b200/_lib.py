@@ -51,6 +51,8 @@ class nufft_callbacks(C.Structure):
         ("nu_weights", C.c_void_p),
         ("u_factor_sep", C.POINTER(C.c_void_p)),
         ("u_factor_dense", C.c_void_p),
+        ("nvrtc_src", C.c_char_p),
+        ("user_data", C.c_void_p),
     ]
 
 

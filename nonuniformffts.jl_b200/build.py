@@ -28,7 +28,8 @@ CFLAGS = ([f"-DNUFFT_DEV_M={DEV_M}"] if DEV_M else []) + ["-O3", "-lineinfo", "-
           "-ccbin", shutil.which("g++") or "g++", "-Xptxas", "-v", "-Xfatbin", "-compress-all"]
 
 # (source, object suffix, extra defines)
-UNITS = [("api.cu", "", []), ("host_plan.cu", "", []), ("binning.cu", "", []), ("deconv.cu", "", []), ("pfft.cu", "", [])]
+UNITS = [("api.cu", "", []), ("host_plan.cu", "", []), ("binning.cu", "", []), ("deconv.cu", "", []), ("pfft.cu", "", []),
+         ("callbacks_jit.cu", "", [])]
 for t in ("float", "double"):
     for c in (0, 1):
         tag = f"_{'f32' if t == 'float' else 'f64'}_{'c' if c else 'r'}"
@@ -71,7 +72,7 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
                 print(f"[nvcc] {obj}", file=sys.stderr)
     (OBJ / "ptxas.log").write_text("\n".join(logs))
     cuda_lib = str(Path(NVCC).resolve().parent.parent / "lib64")
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *objs, "-L" + cuda_lib, "-lcufft",
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *objs, "-L" + cuda_lib, "-lcufft", "-lnvrtc",
            "-Xlinker", "-rpath," + cuda_lib, "-ccbin", shutil.which("g++") or "g++"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

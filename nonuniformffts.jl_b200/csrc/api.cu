@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cmath>
 #include <new>
+#include <vector>
+
 #include "common.cuh"
 #include "spread.cuh"
 #include "interp.cuh"
@@ -213,7 +215,17 @@ int nufft_type1_spread(nufft_plan h, const void *const vp[], const nufft_callbac
     CUDA_TRY(cudaMemsetAsync(p.d_us, 0, (size_t)p.C * p.ncells * zbytes, p.stream));
     NUFFT_COUNT_LAUNCH();
     rec(p, 3);
-    NUFFT_TRY(spread_run(p, vp, cb));
+    {
+        JitCallbacks *j = nullptr;                 // general (run-time compiled) nonuniform callback: v -> cb(v, n) on a copy
+        NUFFT_TRY(jit_callbacks_get(p, cb, &j));
+        if (jit_has_nonuniform(j)) {
+            std::vector<void *> tmp(p.C);
+            NUFFT_TRY(jit_apply_nonuniform(p, j, cb, vp, tmp.data(), true));
+            NUFFT_TRY(spread_run(p, (const void *const *)tmp.data(), cb));
+        } else {
+            NUFFT_TRY(spread_run(p, vp, cb));
+        }
+    }
     rec(p, 4);
     p.ev_rec[1] = true;
     return NUFFT_SUCCESS;
@@ -233,6 +245,11 @@ int nufft_type1_finish(nufft_plan h, void *const uhat[], const nufft_callbacks *
         NUFFT_TRY(fft_forward(p));
         rec(p, 6);
         NUFFT_TRY(deconv_type1_run(p, uhat, cb));
+    }
+    {
+        JitCallbacks *j = nullptr;                 // general uniform callback on the output coefficients, in place
+        NUFFT_TRY(jit_callbacks_get(p, cb, &j));
+        if (jit_has_uniform(j)) NUFFT_TRY(jit_apply_uniform(p, j, cb, nullptr, (void **)uhat, false));
     }
     rec(p, 7);
     p.ev_rec[2] = true;
@@ -255,6 +272,15 @@ int nufft_type2_prepare(nufft_plan h, const void *const uhat[], const nufft_call
     if (!uhat) { set_error("null uhat"); return NUFFT_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(p.device));
     rec(p, 8);
+    std::vector<void *> tmp_u(p.C);
+    {
+        JitCallbacks *j = nullptr;                 // general uniform callback on a copy of the input coefficients
+        NUFFT_TRY(jit_callbacks_get(p, cb, &j));
+        if (jit_has_uniform(j)) {
+            NUFFT_TRY(jit_apply_uniform(p, j, cb, uhat, tmp_u.data(), true));
+            uhat = (const void *const *)tmp_u.data();
+        }
+    }
     if (p.pfft) {
         rec(p, 9);
         NUFFT_TRY(pfft_type2_run(p, uhat, cb));     // zero-padding FFT passes with the deconvolution fused in
@@ -277,6 +303,11 @@ int nufft_type2_interp(nufft_plan h, void *const vp[], const nufft_callbacks *cb
     CUDA_TRY(cudaSetDevice(p.device));
     rec(p, 11);
     NUFFT_TRY(interp_run(p, vp, cb));
+    {
+        JitCallbacks *j = nullptr;                 // general nonuniform callback on the interpolated values, in place
+        NUFFT_TRY(jit_callbacks_get(p, cb, &j));
+        if (jit_has_nonuniform(j)) NUFFT_TRY(jit_apply_nonuniform(p, j, cb, nullptr, (void **)vp, false));
+    }
     rec(p, 12);
     p.ev_rec[4] = true;
     return NUFFT_SUCCESS;

@@ -212,6 +212,8 @@ struct Plan {
     bool ev_rec[32] = {};
     float ms[16] = {};
 
+    void *jit = nullptr;             // run-time compiled callbacks (callbacks_jit.cu)
+
     bool sticky_error = false;
 };
 
@@ -242,6 +244,13 @@ int pfft_type1_run(Plan &p, void *const uhat[], const nufft_callbacks *cb);     
 int pfft_type2_run(Plan &p, const void *const uhat[], const nufft_callbacks *cb);  // deconvolution + padding + FFT
 int fft_forward(Plan &p);
 int fft_backward(Plan &p);
+struct JitCallbacks;                                                       // callbacks_jit.cu
+int jit_callbacks_get(Plan &p, const nufft_callbacks *cb, JitCallbacks **out);
+bool jit_has_nonuniform(const JitCallbacks *j);
+bool jit_has_uniform(const JitCallbacks *j);
+int jit_apply_nonuniform(Plan &p, JitCallbacks *j, const nufft_callbacks *cb, const void *const in[], void *out[], bool tmp);
+int jit_apply_uniform(Plan &p, JitCallbacks *j, const nufft_callbacks *cb, const void *const in[], void *out[], bool tmp);
+void jit_callbacks_free(Plan &p);
 int scan_u32(Plan &p, uint32_t *data, int64_t n, bool inclusive);          // binning.cu (in place prefix sum)
 int binning_ensure_offsets(Plan &p);                                       // binning.cu (column-streaming plans: on demand)
 int binning_coarse_perm(Plan &p, const int32_t **perm);                    // binning.cu (rt plans: reference-order permutation)
@@ -273,7 +282,7 @@ template <typename T> KernelParams<T> make_kernel_params(const Plan &p)
             sum += term;
             if ((double)k * k > q && term < 1e-19 * sum) break;
         }
-        kp.i0_terms = (k + 1 <= 64) ? k + 1 : 0;
+        kp.i0_terms = (k + 1 <= 96) ? k + 1 : 0;       // I0_TABLE entries (kernel_eval.cuh)
     }
     return kp;
 }

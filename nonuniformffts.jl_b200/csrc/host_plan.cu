@@ -514,6 +514,7 @@ int host_plan_init(Plan &p)
 
 void host_plan_free(Plan &p)
 {
+    jit_callbacks_free(p);
     if (p.fft_ok) { cufftDestroy(p.fft_fw); cufftDestroy(p.fft_bw); p.fft_ok = false; }
     pfft_free(p);
     auto f = [](auto *&ptr) { if (ptr) { cudaFree((void *)ptr); ptr = nullptr; } };

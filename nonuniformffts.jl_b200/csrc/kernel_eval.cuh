@@ -39,7 +39,7 @@ __device__ __forceinline__ float fmod_t(float x, float y) { return fmodf(x, y); 
 // two producer warps of the tile kernels (and one lane per point elsewhere) Float64 Direct evaluation was latency-bound and
 // cost more than the spreading itself; W independent Horner chains keep the FP64 pipe busy instead.  nterms is chosen on the
 // host from the plan's beta (make_kernel_params); 0 = beta too large for the table, use the library function.
-constexpr int I0_TABLE = 64;
+constexpr int I0_TABLE = 96;
 static __constant__ double c_i0_coef[I0_TABLE] = {
     1.0, 1.0, 0.25, 0.027777777777777776,
     0.001736111111111111, 6.944444444444444e-05, 1.9290123456790124e-06, 3.936759889140842e-08,
@@ -56,7 +56,15 @@ static __constant__ double c_i0_coef[I0_TABLE] = {
     6.48906947264458e-123, 2.7026528415845812e-126, 1.0810611366338324e-129, 4.156328860568368e-133,
     1.5371038685533903e-136, 5.472067883778535e-140, 1.876566489635986e-143, 6.203525585573507e-147,
     1.9781650464201234e-150, 6.088535076700903e-154, 1.8099093569265468e-157, 5.199394877697635e-161,
-    1.4442763549160097e-164, 3.8814199272131406e-168, 1.0097346324695995e-171, 2.544052991860921e-175};
+    1.4442763549160097e-164, 3.8814199272131406e-168, 1.0097346324695995e-171, 2.544052991860921e-175,
+    6.211066874660451e-179, 1.4700749999196336e-182, 3.374827823506964e-186, 7.517994705963386e-190,
+    1.6258639069990022e-193, 3.414963047676963e-197, 6.969312342197885e-201, 1.3825257572302885e-204,
+    2.6669092539164517e-208, 5.004521024425692e-212, 9.139008444897175e-216, 1.6247126124261642e-219,
+    2.812868096305686e-223, 4.744253830841096e-227, 7.797918854110941e-231, 1.2494662480549497e-234,
+    1.952291012585859e-238, 2.975599775317572e-242, 4.425341724148679e-246, 6.423779538610364e-250,
+    9.103995944742579e-254, 1.2600686428709451e-257, 1.7037163911180977e-261, 2.2509134510742472e-265,
+    2.9066547663665382e-269, 3.6695553167106908e-273, 4.530315205815668e-277, 5.470734459383731e-281,
+    6.463533151445807e-285, 7.473156609371958e-289, 8.457624048632819e-293, 9.371328585742735e-297};
 template <int W> __device__ __forceinline__ void i0_series(const double (&z)[W], double (&out)[W], int nterms)
 {
     double q[W], acc[W];

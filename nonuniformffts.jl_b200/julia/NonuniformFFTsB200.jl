@@ -72,6 +72,8 @@ mutable struct NufftCallbacks
     nu_weights::Ptr{Cvoid}
     u_factor_sep::Ptr{Ptr{Cvoid}}
     u_factor_dense::Ptr{Cvoid}
+    nvrtc_src::Cstring          # optional CUDA C++ source of general callbacks (compiled with NVRTC once per plan)
+    user_data::Ptr{Cvoid}       # device pointer handed to them
 end
 
 """
@@ -158,10 +160,15 @@ end
 
 function _callbacks(cb)
     cb === nothing && return C_NULL
-    # cb = (nonuniform = weights::DeviceVector | nothing, uniform = factor::DeviceArray | nothing)
+    # cb = (nonuniform = weights::DeviceVector | nothing, uniform = factor::DeviceArray | nothing,
+    #       source = CUDA C++ source of general callbacks | nothing, user_data = DeviceArray | nothing)
+    src = get(cb, :source, nothing)
+    usr = get(cb, :user_data, nothing)
     Ref(NufftCallbacks(UInt32(sizeof(NufftCallbacks)),
         cb.nonuniform === nothing ? C_NULL : devptr(cb.nonuniform), C_NULL,
-        cb.uniform === nothing ? C_NULL : devptr(cb.uniform)))
+        cb.uniform === nothing ? C_NULL : devptr(cb.uniform),
+        src === nothing ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, src),     # `src` must stay rooted during the call
+        usr === nothing ? C_NULL : devptr(usr)))
 end
 
 """    exec_type1!(ûs, p, vp; callbacks)   — src/NonuniformFFTs.jl:148-195"""

@@ -113,6 +113,12 @@ class NUFFTCallbacks:
     uniform: dense tensor f[I] of shape plan.shape, or a tuple of D 1-D tensors (separable factor)."""
     nonuniform: Optional[torch.Tensor] = None
     uniform: object = None
+    # general callbacks (the reference's arbitrary closures): CUDA C++ source compiled with NVRTC once per plan, defining
+    # nufft_cb_nonuniform(nufft_cell (&v)[NUFFT_C], long long n, const void *user) after `#define NUFFT_HAS_NONUNIFORM 1`
+    # and / or nufft_cb_uniform(nufft_cplx (&w)[NUFFT_C], const int (&idx)[3], const void *user) after
+    # `#define NUFFT_HAS_UNIFORM 1` (include/nufft_b200.h); user_data: optional device tensor handed to them
+    source: Optional[str] = None
+    user_data: Optional[torch.Tensor] = None
 
 
 _REAL = {torch.float32: torch.float32, torch.float64: torch.float64,
@@ -261,11 +267,19 @@ class PlanNUFFT:
             raise ArgumentError(f"{what} must be contiguous")
 
     def _callbacks(self, cb: Optional[NUFFTCallbacks]):
-        if cb is None or (cb.nonuniform is None and cb.uniform is None):
+        if cb is None or (cb.nonuniform is None and cb.uniform is None and not cb.source):
             return None, None
         s = nufft_callbacks()
         s.struct_size = C.sizeof(nufft_callbacks)
         keep = []
+        if cb.source:
+            src = cb.source.encode()
+            s.nvrtc_src = src
+            keep.append(src)
+            if cb.user_data is not None:
+                self._check_dev(cb.user_data, "callback user data")
+                s.user_data = cb.user_data.data_ptr()
+                keep.append(cb.user_data)
         if cb.nonuniform is not None:
             w = cb.nonuniform
             self._check_dev(w, "nonuniform callback weights")

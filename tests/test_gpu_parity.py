@@ -173,6 +173,74 @@ def test_callbacks(nufft, oracle_mod, dtype):
         run_case(nufft, oracle_mod, dtype, (64, 32, 16), 64 * 32 * 16 // 3, callbacks=True, method=method, seed=11)
 
 
+JIT_SRC = r"""
+#define NUFFT_HAS_NONUNIFORM 1
+__device__ void nufft_cb_nonuniform(nufft_cell (&v)[NUFFT_C], long long n, const void *user)
+{
+    const nufft_real s = (nufft_real)1 + (nufft_real)0.25 * (nufft_real)(n % 7);
+    const nufft_cell a = v[0];                       // swap the two components and scale by s(n)
+    v[0] = v[1]; v[1] = a;
+#if NUFFT_IS_COMPLEX
+    v[0].x *= s; v[0].y *= s; v[1].x *= s; v[1].y *= s;
+#else
+    v[0] *= s; v[1] *= s;
+#endif
+}
+#define NUFFT_HAS_UNIFORM 1
+__device__ void nufft_cb_uniform(nufft_cplx (&w)[NUFFT_C], const int (&idx)[3], const void *user)
+{
+    const nufft_real *table = (const nufft_real *)user;      // user data: one factor per first-dimension index
+    const nufft_real f = table[idx[0]] / (nufft_real)(1 + idx[1] + 2 * idx[2]);
+    for (int c = 0; c < NUFFT_C; ++c) { w[c].x *= f; w[c].y *= f; }
+}
+"""
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.float64])
+def test_runtime_compiled_callbacks(nufft, oracle_mod, dtype):
+    """General callbacks (arbitrary closures in the reference, src/plan.jl:146-164; test/callbacks.jl) as CUDA source compiled
+    with NVRTC: nonuniform swaps the two components and scales by s(n); uniform multiplies by f(idx).  Checked against the
+    oracle driven with the equivalent weights / dense factor and swapped inputs (type 1) / swapped outputs (type 2)."""
+    import torch
+    dtype = np.dtype(dtype)
+    rt, ct = real_of(dtype), complex_of(dtype)
+    rng = np.random.default_rng(7)
+    dims, Np, C = (24, 20, 16), 9000, 2
+    xs = make_points(rng, 3, Np, rt)
+    vps = [make_values(rng, Np, dtype) for _ in range(C)]
+    op = oracle_mod.OraclePlan(dtype, dims, m=4, sigma=2.0, kernel="backwards_kaiser_bessel", evalmode="fast", ntransforms=C, block_size=None)
+    gp = gpu_plan(nufft, dtype, dims, m=4, sigma=2.0, ntransforms=C)
+    op.set_points(xs)
+    gp.set_points(tuple(to_dev(x) for x in xs))
+    s_n = (1 + 0.25 * (np.arange(Np) % 7)).astype(rt)
+    table = (0.5 + rng.random(op.size[0])).astype(rt)
+    i0, i1, i2 = np.meshgrid(np.arange(op.size[0]), np.arange(op.size[1]), np.arange(op.size[2]), indexing="ij")
+    fac = (table[i0] / (1 + i1 + 2 * i2)).astype(rt).transpose(2, 1, 0).copy()        # numpy layout = size[::-1]
+    cb = nufft.NUFFTCallbacks(source=JIT_SRC, user_data=to_dev(table))
+    tol = TOL[rt]
+    # type 1: oracle with swapped inputs, weights s(n), dense factor
+    ref1 = op.exec_type1([vps[1], vps[0]], nu_weights=s_n, u_factor=fac)
+    outs = [torch.empty(gp.shape, dtype=gp.complex_dtype, device="cuda") for _ in range(C)]
+    dv = [to_dev(v) for v in vps]
+    gp.exec_type1(outs, dv, callbacks=cb)
+    for c in range(C):
+        assert torch.equal(dv[c].cpu(), torch.from_numpy(vps[c])), "exec_type1 modified its input"
+        assert l2_error(outs[c].cpu().numpy(), ref1[c]) <= tol
+    # type 2: oracle, then swap the outputs (the callback runs on the interpolated values)
+    uks = [make_values(rng, int(np.prod(op.size)), ct).reshape(op.size[::-1]) for _ in range(C)]
+    ref2 = op.exec_type2(uks, nu_weights=s_n, u_factor=fac)
+    duk = [to_dev(u) for u in uks]
+    vout = [torch.empty(Np, dtype=gp.dtype, device="cuda") for _ in range(C)]
+    gp.exec_type2(vout, duk, callbacks=cb)
+    for c in range(C):
+        assert torch.equal(duk[c].cpu(), torch.from_numpy(uks[c])), "exec_type2 modified its input"
+        assert l2_error(vout[c].cpu().numpy(), ref2[1 - c]) <= tol
+    # a source that does not compile is an ArgumentError with the compiler log
+    with pytest.raises(nufft.ArgumentError):
+        gp.exec_type1(outs, dv, callbacks=nufft.NUFFTCallbacks(source="#define NUFFT_HAS_NONUNIFORM 1\nthis is not C++"))
+    gp.close()
+
+
 def test_fftshift(nufft, oracle_mod):
     run_case(nufft, oracle_mod, np.complex128, (33, 40), 3000, fftshift=True, seed=12)
     run_case(nufft, oracle_mod, np.complex64, (16, 17, 18), 3000, fftshift=True, seed=13)

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cfg", default="c4")
 ap.add_argument("--np", type=int, default=1 << 24)
 ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--fast", action="store_true", help="FastApproximation instead of the reference's GPU default (Direct)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 g = torch.Generator(device="cuda").manual_seed(4)
@@ -22,7 +23,8 @@ if a.cfg == "c4":
     N, C, npts = 256, 3, a.np
     xs = [torch.randn(npts, generator=g, device=dev, dtype=torch.float64) for _ in range(3)]
     vp = [torch.randn(npts, generator=g, device=dev, dtype=torch.float64) for _ in range(C)]
-    plan = nb.PlanNUFFT(torch.float64, (N,) * 3, m=8, sigma=2.0, kernel=nb.KaiserBesselKernel(), ntransforms=C, timer=True)
+    plan = nb.PlanNUFFT(torch.float64, (N,) * 3, m=8, sigma=2.0, kernel=nb.KaiserBesselKernel(), ntransforms=C, timer=True,
+                        kernel_evalmode=nb.FastApproximation() if a.fast else nb.Direct())
     out1 = [torch.empty((N, N, N // 2 + 1), dtype=torch.complex128, device=dev) for _ in range(C)]
     out2 = [torch.empty(npts, dtype=torch.float64, device=dev) for _ in range(C)]
 else:
