@@ -10,6 +10,7 @@
 
 namespace nufft {
 
+constexpr int I0_MAX_TERMS = 96;   // per-dimension table of the I0 power series behind the polynomial coefficients (Direct KB)
 constexpr int MAX_M = 12;          // largest half support instantiated
 constexpr int MIN_M = 2;
 constexpr int MAX_W = 2 * MAX_M;
@@ -107,9 +108,9 @@ template <typename T> struct KernelParams {
     T tau[3];        // Gaussian 2 sigma^2
     T dx[3];         // 2pi / N
     const T *cs;     // device: per dim d a block of CS_STRIDE values:
-                     //   [ (M+4)*2M polynomial coefs, layout [p][j] | M Gaussian exponentials ]
-    int cs_stride;   // = (M+4)*2M + M
-    int i0_terms;    // Float64 Direct KB: terms of the I0 power series (kernel_eval.cuh), 0 = library cyl_bessel_i0
+                     //   [ (M+4)*2M polynomial coefs, layout [p][j] | M Gaussian exponentials | I0_MAX_TERMS series coefs ]
+    int cs_stride;   // = (M+4)*2M + M + I0_MAX_TERMS
+    int i0_terms;    // Direct KB: terms of the I0 power series to use (kernel_eval.cuh), 0 = library cyl_bessel_i0
 };
 
 // ---- geometry of bins / tiles handed to spreading & interpolation kernels ---------------------
@@ -270,19 +271,19 @@ template <typename T> KernelParams<T> make_kernel_params(const Plan &p)
     kp.cs = (const T *)p.d_cs;
     kp.cs_stride = p.cs_stride;
     kp.i0_terms = 0;
-    if (sizeof(T) == 8 && p.opts.kernel == NUFFT_KERNEL_KAISER_BESSEL) {
+    if (p.opts.kernel == NUFFT_KERNEL_KAISER_BESSEL) {
         double bmax = 0;
         for (int d = 0; d < 3; ++d) bmax = p.kp_beta[d] > bmax ? p.kp_beta[d] : bmax;
-        const double q = 0.25 * bmax * bmax;
+        const double q = 0.25 * bmax * bmax, eps = sizeof(T) == 8 ? 1e-19 : 1e-10;
         double term = 1, sum = 1;
         int k = 0;
-        while (k < 200) {
+        while (k < 400) {
             ++k;
             term *= q / ((double)k * (double)k);
             sum += term;
-            if ((double)k * k > q && term < 1e-19 * sum) break;
+            if ((double)k * k > q && term < eps * sum) break;
         }
-        kp.i0_terms = (k + 1 <= 96) ? k + 1 : 0;       // I0_TABLE entries (kernel_eval.cuh)
+        kp.i0_terms = (k + 1 <= I0_MAX_TERMS) ? k + 1 : 0;
     }
     return kp;
 }

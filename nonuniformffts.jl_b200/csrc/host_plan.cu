@@ -117,6 +117,15 @@ static void build_kernel_dim(Plan &p, int d, std::vector<T> &cs_block, std::vect
             for (int q = 0; q < np; ++q) cs_block[(size_t)q * W + (j - 1)] = ys[q];
         }
         p.h_shape[d] = (double)beta;
+        if (kind == NUFFT_KERNEL_KAISER_BESSEL) {
+            // I0(beta sqrt(t)) = sum_k c_k t^k, c_k = (beta^2 / 4)^k / (k!)^2 (Direct evaluation, kernel_eval.cuh)
+            const double q = 0.25 * (double)beta * (double)beta;
+            double term = 1.0;
+            for (int k = 0; k < I0_MAX_TERMS; ++k) {
+                if (k > 0) term *= q / ((double)k * (double)k);
+                cs_block[(size_t)np * W + M + k] = (T)term;
+            }
+        }
     } else if (kind == NUFFT_KERNEL_GAUSSIAN) {
         T ell = user_param ? (T)p.opts.kernel_param
                            : (T)std::sqrt((double)(sigma_d * (T)M / ((T)2 * sigma_d - (T)1)) / M_PI);
@@ -412,7 +421,7 @@ int host_plan_init(Plan &p)
     p.nspec = p.Nspec[0] * p.Nspec[1] * p.Nspec[2];
     p.nkept = p.nk[0] * p.nk[1] * p.nk[2];
     if (p.ncells >= ((int64_t)1 << 31)) { set_error("oversampled grid has >= 2^31 cells (32-bit cell indices)"); return NUFFT_ERR_UNSUPPORTED; }
-    p.cs_stride = (p.M + 4) * 2 * p.M + p.M;
+    p.cs_stride = (p.M + 4) * 2 * p.M + p.M + I0_MAX_TERMS;
 
     NUFFT_TRY(p.f64 ? upload_tables<double>(p) : upload_tables<float>(p));
 
