@@ -173,6 +173,40 @@ def test_callbacks(nufft, oracle_mod, dtype):
         run_case(nufft, oracle_mod, dtype, (64, 32, 16), 64 * 32 * 16 // 3, callbacks=True, method=method, seed=11)
 
 
+def _sweep_cases():
+    """Corner cases of the column-streaming kernels: two z segments (oversampled z extent above 256), odd grid extents,
+    point counts around a work-item boundary, degenerate / clustered point sets, Direct evaluation, plus seeded random draws."""
+    cases = [
+        dict(dims=(8, 8, 140), Np=30000, sigma=2.0),
+        dict(dims=(10, 9, 200), Np=20011, sigma=1.5),
+        dict(dims=(12, 12, 12), Np=511, sigma=2.0),
+        dict(dims=(12, 12, 12), Np=512, sigma=2.0),
+        dict(dims=(12, 12, 12), Np=513, sigma=2.0),
+        dict(dims=(9, 31, 17), Np=33, sigma=2.0),
+        dict(dims=(50, 8, 8), Np=100000, sigma=2.0, dist="blobs"),
+        dict(dims=(16, 16, 16), Np=40000, sigma=2.0, dist="onecell", C=3),
+        dict(dims=(21, 13, 34), Np=25000, sigma=1.25, f32_relaxed=True, kernel="kaiser_bessel", evalmode="direct"),
+        dict(dims=(18, 18, 18), Np=9999, sigma=2.0, kernel="bspline"),
+        dict(dims=(18, 18, 18), Np=9999, sigma=2.0, kernel="gaussian", evalmode="direct"),
+    ]
+    rng = np.random.default_rng(2026)
+    for _ in range(10):
+        dims = tuple(int(v) for v in rng.integers(8, 48, size=3))
+        cases.append(dict(dims=dims, Np=int(rng.integers(1, 60000)), sigma=float(rng.choice([1.25, 1.5, 2.0])), f32_relaxed=True,
+                          dist=str(rng.choice(["uniform", "clustered", "blobs"])), C=int(rng.integers(1, 3)),
+                          callbacks=bool(rng.integers(0, 2)), fftshift=bool(rng.integers(0, 2)), seed=int(rng.integers(1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _sweep_cases(), ids=lambda c: "x".join(map(str, c["dims"])) + f"-{c['Np']}")
+def test_column_streaming_sweep(nufft, oracle_mod, monkeypatch, case):
+    monkeypatch.setenv("NUFFT_B200_CS", "1")
+    monkeypatch.setenv("NUFFT_B200_CS_DENSITY", "0")
+    kw = dict(case)
+    dims, Np, seed = kw.pop("dims"), kw.pop("Np"), kw.pop("seed", 5)
+    run_case(nufft, oracle_mod, np.complex64, dims, Np, method="shared_memory", seed=seed, **kw)
+
+
 JIT_SRC = r"""
 #define NUFFT_HAS_NONUNIFORM 1
 __device__ void nufft_cb_nonuniform(nufft_cell (&v)[NUFFT_C], long long n, const void *user)
