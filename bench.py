@@ -298,6 +298,20 @@ def run_ours(args):
     ms_t1 = timed(t1_only, K) / K
     ms_t2 = timed(t2_only, K) / K
 
+    # clustered points (north_star: "uniform-random and clustered"): Gaussian cloud, sigma = 1 rad around x = 0 (folded by
+    # set_points), same values / spectrum; same protocol, reported beside the headline numbers
+    rng_c = np.random.default_rng(1000 + rank)
+    xs_c = [torch.from_numpy(rng_c.standard_normal(npts, dtype=np.float32)).to(dev) for _ in range(3)]
+    def t1_clustered():
+        plan.set_points(tuple(xs_c)); plan.exec_type1(out1_d, vp_d)
+    def t2_clustered():
+        plan.set_points(tuple(xs_c)); plan.exec_type2(out2_d, uk_d)
+    t1_clustered(); t2_clustered()
+    ms_t1c = timed(t1_clustered, K) / K
+    ms_t2c = timed(t2_clustered, K) / K
+    timer_c = plan.timer
+    del xs_c
+
     for _ in range(2):
         step_e2e()
     e2e_drain()
@@ -356,6 +370,9 @@ def run_ours(args):
                        if world > 1 else "single GPU"},
             "type1_points_per_s": npts * world / (ms_t1 * 1e-3), "type2_points_per_s": npts * world / (ms_t2 * 1e-3),
             "type1_ms": ms_t1, "type2_ms": ms_t2,
+            "clustered": {"points": "Gaussian cloud, sigma = 1 rad (folded), Np = 2^24 per GPU", "type1_ms": ms_t1c, "type2_ms": ms_t2c,
+                          "type1_points_per_s": npts * world / (ms_t1c * 1e-3), "type2_points_per_s": npts * world / (ms_t2c * 1e-3),
+                          "stage_ms": timer_c},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K,

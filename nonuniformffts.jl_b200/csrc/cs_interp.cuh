@@ -1,4 +1,5 @@
-// cs_interp.cuh — K-interp, column-streaming variant (3-D, HalfSupport(4), ComplexF32).  Mirror image of cs_spread.cuh;
+// cs_interp.cuh — K-interp, column-streaming variant (3-D, HalfSupport(4), Float32 complex or real data).  Mirror image of
+// cs_spread.cuh (real data: two consecutive z planes per packed register, as there);
 // replaces src/interpolation/gpu.jl:211-395 for this configuration class (same sums, different order).
 //
 // A warp walks through a chunk of the points ordered by (z segment, column of 4 x 4 cells, layer of 4 cells) and keeps
@@ -47,13 +48,22 @@ __device__ __forceinline__ u64 ldg_cell(const float2 *p)
     asm volatile("ld.global.nc.b64 %0, [%1];" : "=l"(v) : "l"(p));
     return v;
 }
+__device__ __forceinline__ float ldg_cell(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 
-template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
+template <bool CPLX>                       // complex / real Float32 data (one instantiation per translation unit)
 __global__ void __launch_bounds__(32 * NWARP)
 cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
                  const float4 *__restrict__ prec, MutPtrPack vp, int C,
-                 const float2 *__restrict__ us, int64_t ncells, float prefactor, const float *__restrict__ nu_weights)
+                 const typename CellOf<float, CPLX>::type *__restrict__ us, int64_t ncells, float prefactor,
+                 const float *__restrict__ nu_weights)
 {
+    using Cell = typename CellOf<float, CPLX>::type;
+    constexpr int NR = Win<CPLX>::NR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH][REC_F]
     float *stage_all = rec_all + NWARP * BATCH * REC_F;                      // [NWARP][STAGE_F] coordinates / index staging
@@ -65,7 +75,7 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
     const unsigned FULL = 0xffffffffu;
     float *rec_w = rec_all + warp * BATCH * REC_F;
     u64 *part_w = part_all + warp * HALF * PART_LD;
-    u64 *hst_w = hst_all + warp * 16 * 32 + lane;
+    Cell *hst_w = reinterpret_cast<Cell *>(hst_all + warp * 16 * 32) + lane;
     float4 *st_x = reinterpret_cast<float4 *>(stage_all + warp * STAGE_F) + lane;      // folded (x, y, z, -) of the point
     int32_t *st_n = reinterpret_cast<int32_t *>(stage_all + warp * STAGE_F + 192) + lane;
 
@@ -77,11 +87,11 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
     const int plane = Nx * Ny;
     const unsigned long long pol = l2_evict_first_policy();
 
-    u64 G[4][P];                                       // window: planes COL * wl - 3 .. COL * wl + 7
+    u64 G[4][NR];                                      // window: planes COL * wl - 3 .. COL * wl + 7
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int i = 0; i < P; ++i) G[k][i] = 0ull;
+        for (int i = 0; i < NR; ++i) G[k][i] = 0ull;
 
     while (true) {
         int item = 0;
@@ -93,27 +103,43 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
         const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
 
         for (int c = 0; c < C; ++c) {
-            float2 *vc = (float2 *)vp.p[c];
-            const float2 *u = us + (int64_t)c * ncells;
+            Cell *vc = (Cell *)vp.p[c];
+            const Cell *u = us + (int64_t)c * ncells;
             int wcol = -1, wl = 0;                         // column id (cy << 16 | cx), layer
             int goff[4] = {0, 0, 0, 0};                    // cell offsets of the lane's 4 columns inside a z plane
 
             auto request_ahead = [&]() {                   // planes P .. P + 3 relative to the window (next layer's new planes)
 #pragma unroll
                 for (int i = 0; i < COL; ++i) {
-                    const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + P + i, Nz) * plane;
+                    const Cell *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + P + i, Nz) * plane;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) cp_async_cell<8>(hst_w + (4 * i + k) * 32, pl + goff[k]);
+                    for (int k = 0; k < 4; ++k) cp_async_cell<(int)sizeof(Cell)>(hst_w + (4 * i + k) * 32, pl + goff[k]);
                 }
                 cp_async_commit();
             };
             auto load_all = [&]() {
                 cp_async_wait0();                          // a request of the previous window may be in flight
+                if constexpr (CPLX) {
 #pragma unroll
-                for (int i = 0; i < P; ++i) {
-                    const float2 *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + i, Nz) * plane;
+                    for (int i = 0; i < P; ++i) {
+                        const Cell *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + i, Nz) * plane;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) G[k][i] = ldg_cell(pl + goff[k]);
+                        for (int k = 0; k < 4; ++k) G[k][i] = ldg_cell(pl + goff[k]);
+                    }
+                } else {                                   // planes 2j, 2j + 1 share register j; the 12th plane is padding
+                    float f[4][P + 1];
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        const Cell *pl = u + (int64_t)wrap1(COL * wl - (M - 1) + i, Nz) * plane;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) f[k][i] = ldg_cell(pl + goff[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        f[k][P] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NR; ++j) G[k][j] = pk2(f[k][2 * j], f[k][2 * j + 1]);
+                    }
                 }
                 request_ahead();
             };
@@ -121,10 +147,17 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                 cp_async_wait0();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
+                    if constexpr (CPLX) {
 #pragma unroll
-                    for (int i = 0; i < P - COL; ++i) G[k][i] = G[k][i + COL];
+                        for (int i = 0; i < P - COL; ++i) G[k][i] = G[k][i + COL];
 #pragma unroll
-                    for (int i = 0; i < COL; ++i) G[k][P - COL + i] = hst_w[(4 * i + k) * 32];
+                        for (int i = 0; i < COL; ++i) G[k][P - COL + i] = *reinterpret_cast<const u64 *>(hst_w + (4 * i + k) * 32);
+                    } else {                               // old planes 4 .. 10 -> 0 .. 6; plane 6 shares register 3 with new plane 7
+                        G[k][0] = G[k][2]; G[k][1] = G[k][3]; G[k][2] = G[k][4];
+                        G[k][3] = pk2(unpk2(G[k][5]).x, hst_w[(4 * 0 + k) * 32]);
+                        G[k][4] = pk2(hst_w[(4 * 1 + k) * 32], hst_w[(4 * 2 + k) * 32]);
+                        G[k][5] = pk2(hst_w[(4 * 3 + k) * 32], 0.f);
+                    }
                 }
                 ++wl;
                 request_ahead();
@@ -201,13 +234,22 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                         PointRec A = load_rec(rec_w + p0 * REC_F, ls);
 #pragma unroll 1
                         for (int p = p0; p < p1; ++p) {
-                            const float wz[P] = {A.z0.x, A.z0.y, A.z0.z, A.z0.w, A.z1.x, A.z1.y, A.z1.z, A.z1.w, A.z2.x, A.z2.y, A.z2.z};
                             u64 tk[4] = {0ull, 0ull, 0ull, 0ull};
+                            if constexpr (CPLX) {
+                                const float wz[P] = {A.z0.x, A.z0.y, A.z0.z, A.z0.w, A.z1.x, A.z1.y, A.z1.z, A.z1.w, A.z2.x, A.z2.y, A.z2.z};
 #pragma unroll
-                            for (int i = 0; i < P; ++i) {
-                                const u64 wzz = pk2(wz[i], wz[i]);
+                                for (int i = 0; i < P; ++i) {
+                                    const u64 wzz = pk2(wz[i], wz[i]);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][i], wzz, tk[k]);
+                                    for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][i], wzz, tk[k]);
+                                }
+                            } else {                       // (even planes, odd planes) partial sums; added up after the reduction
+                                const u64 wz[6] = {pk2(A.z0.x, A.z0.y), pk2(A.z0.z, A.z0.w), pk2(A.z1.x, A.z1.y),
+                                                   pk2(A.z1.z, A.z1.w), pk2(A.z2.x, A.z2.y), pk2(A.z2.z, A.z2.w)};      // z2.w = 0
+#pragma unroll
+                                for (int j = 0; j < 6; ++j)
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) tk[k] = ffma2(G[k][j], wz[j], tk[k]);
                             }
                             const u64 w01 = fmul2(pk2(A.wx, A.wx), pk2(A.wy.x, A.wy.y));
                             const u64 w23 = fmul2(pk2(A.wx, A.wx3), pk2(A.wy.z, A.wy.w));
@@ -237,7 +279,8 @@ cs_interp_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                         if (lane >= h0 && lane < h1) {
                             const float2 rv = unpk2(res);
                             const float scale = prefactor * (nu_weights ? nu_weights[n_mine] : 1.f);
-                            __stcs(vc + n_mine, make_float2(rv.x * scale, rv.y * scale));     // streaming store: written once
+                            if constexpr (CPLX) __stcs(vc + n_mine, make_float2(rv.x * scale, rv.y * scale));     // streaming store: written once
+                            else __stcs(vc + n_mine, (rv.x + rv.y) * scale);
                         }
                     }
                     __syncwarp();

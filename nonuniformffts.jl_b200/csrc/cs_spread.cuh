@@ -1,4 +1,5 @@
-// cs_spread.cuh — K-spread, column-streaming variant (3-D, HalfSupport(4), ComplexF32): no shared-memory tile at all.
+// cs_spread.cuh — K-spread, column-streaming variant (3-D, HalfSupport(4), Float32 complex or real data): no shared-memory
+// tile at all.
 // Replaces src/spreading/gpu.jl:237-434 for this configuration class (same sums, different order).
 //
 // set_points orders the points by (z segment of 64 cells, column of 4 x 4 cells in (x, y), layer of 4 cells in z).  A
@@ -123,6 +124,16 @@ __device__ __forceinline__ void red_cell(float2 *p, u64 v)
     const float2 f = unpk2(v);
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(f.x), "f"(f.y) : "memory");
 }
+__device__ __forceinline__ void red_cell(float *p, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// u64 registers per (x, y) column of the window: complex data one packed (re, im) cell per plane; real data two consecutive
+// planes per register (planes 2j, 2j + 1; the 12th plane is padding and stays zero)
+template <bool CPLX> struct Win {
+    static constexpr int NR = CPLX ? P : (P + 1) / 2;
+};
 
 struct PointRec {
     float2 hv;
@@ -141,32 +152,51 @@ __device__ __forceinline__ PointRec load_rec(const float *r, const rt::LaneSlots
     q.z0 = zq[0]; q.z1 = zq[1]; q.z2 = zq[2];
     return q;
 }
-// G[k][i] += value x (wx wy)_k x wz_i : 6 FMUL2 + 44 FFMA2
-__device__ __forceinline__ void accumulate(u64 (&G)[4][P], const PointRec &q)
+// complex data: G[k][i] += value x (wx wy)_k x wz_i : 6 FMUL2 + 44 FFMA2
+// real data:    G[k][j] += (value wx wy)_k x (wz_2j, wz_2j+1) : 4 FMUL2 + 24 FFMA2
+template <bool CPLX>
+__device__ __forceinline__ void accumulate(u64 (&G)[4][Win<CPLX>::NR], const PointRec &q)
 {
     const u64 w01 = fmul2(pk2(q.wx, q.wx), pk2(q.wy.x, q.wy.y));
     const u64 w23 = fmul2(pk2(q.wx, q.wx3), pk2(q.wy.z, q.wy.w));
-    const float2 wa = unpk2(w01), wb = unpk2(w23);
-    const u64 v2 = pk2(q.hv.x, q.hv.y);
-    const u64 a0 = fmul2(v2, pk2(wa.x, wa.x)), a1 = fmul2(v2, pk2(wa.y, wa.y));
-    const u64 a2 = fmul2(v2, pk2(wb.x, wb.x)), a3 = fmul2(v2, pk2(wb.y, wb.y));
-    const float wz[P] = {q.z0.x, q.z0.y, q.z0.z, q.z0.w, q.z1.x, q.z1.y, q.z1.z, q.z1.w, q.z2.x, q.z2.y, q.z2.z};
+    if constexpr (CPLX) {
+        const float2 wa = unpk2(w01), wb = unpk2(w23);
+        const u64 v2 = pk2(q.hv.x, q.hv.y);
+        const u64 a0 = fmul2(v2, pk2(wa.x, wa.x)), a1 = fmul2(v2, pk2(wa.y, wa.y));
+        const u64 a2 = fmul2(v2, pk2(wb.x, wb.x)), a3 = fmul2(v2, pk2(wb.y, wb.y));
+        const float wz[P] = {q.z0.x, q.z0.y, q.z0.z, q.z0.w, q.z1.x, q.z1.y, q.z1.z, q.z1.w, q.z2.x, q.z2.y, q.z2.z};
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const u64 wzz = pk2(wz[i], wz[i]);
-        G[0][i] = ffma2(a0, wzz, G[0][i]);
-        G[1][i] = ffma2(a1, wzz, G[1][i]);
-        G[2][i] = ffma2(a2, wzz, G[2][i]);
-        G[3][i] = ffma2(a3, wzz, G[3][i]);
+        for (int i = 0; i < P; ++i) {
+            const u64 wzz = pk2(wz[i], wz[i]);
+            G[0][i] = ffma2(a0, wzz, G[0][i]);
+            G[1][i] = ffma2(a1, wzz, G[1][i]);
+            G[2][i] = ffma2(a2, wzz, G[2][i]);
+            G[3][i] = ffma2(a3, wzz, G[3][i]);
+        }
+    } else {
+        const u64 vv = pk2(q.hv.x, q.hv.x);
+        const float2 wa = unpk2(fmul2(w01, vv)), wb = unpk2(fmul2(w23, vv));
+        const u64 a0 = pk2(wa.x, wa.x), a1 = pk2(wa.y, wa.y), a2 = pk2(wb.x, wb.x), a3 = pk2(wb.y, wb.y);
+        const u64 wz[6] = {pk2(q.z0.x, q.z0.y), pk2(q.z0.z, q.z0.w), pk2(q.z1.x, q.z1.y),
+                           pk2(q.z1.z, q.z1.w), pk2(q.z2.x, q.z2.y), pk2(q.z2.z, q.z2.w)};      // z2.w = 0 (record padding)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            G[0][j] = ffma2(a0, wz[j], G[0][j]);
+            G[1][j] = ffma2(a1, wz[j], G[1][j]);
+            G[2][j] = ffma2(a2, wz[j], G[2][j]);
+            G[3][j] = ffma2(a3, wz[j], G[3][j]);
+        }
     }
 }
 
-template <typename Inst>                   // instantiated only by the ComplexF32 translation unit
+template <bool CPLX>                       // complex / real Float32 data (one instantiation per translation unit)
 __global__ void __launch_bounds__(32 * NWARP)       // (no min-blocks hint: with it ptxas renames the accumulators and adds ~30 MOVs per point)
 cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
                  const float4 *__restrict__ prec, PtrPack vp, int C,
-                 float2 *__restrict__ us, int64_t ncells, const float *__restrict__ nu_weights)
+                 typename CellOf<float, CPLX>::type *__restrict__ us, int64_t ncells, const float *__restrict__ nu_weights)
 {
+    using Cell = typename CellOf<float, CPLX>::type;
+    constexpr int NR = Win<CPLX>::NR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH][REC_F]
     float *stage_all = rec_all + NWARP * BATCH * REC_F;                      // [NWARP][STAGE_F]
@@ -188,11 +218,11 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
     const int plane = Nx * Ny;
     const unsigned long long pol = l2_evict_first_policy();
 
-    u64 G[4][P];
+    u64 G[4][NR];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int i = 0; i < P; ++i) G[k][i] = 0ull;
+        for (int i = 0; i < NR; ++i) G[k][i] = 0ull;
 
     while (true) {
         int item = 0;
@@ -204,8 +234,8 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
         const int nbatches = (k1 - k0 + BATCH - 1) / BATCH;
 
         for (int c = 0; c < C; ++c) {
-            const float2 *vc = (const float2 *)vp.p[c];
-            float2 *u = us + (int64_t)c * ncells;
+            const Cell *vc = (const Cell *)vp.p[c];
+            Cell *u = us + (int64_t)c * ncells;
             // ---- window state ---------------------------------------------------------------------------------------
             int wcol = -1, wl = 0;                         // column id (cy << 16 | cx), layer
             int goff[4] = {0, 0, 0, 0};                    // cell offsets of the lane's 4 columns inside a z plane
@@ -215,10 +245,22 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
 #pragma unroll
                 for (int i = I0; i < I1; ++i) {
                     const int gz = wrap1(COL * wl - (M - 1) + i, Nz);
-                    float2 *pl = u + (int64_t)gz * plane;
+                    Cell *pl = u + (int64_t)gz * plane;
+                    if constexpr (CPLX) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) red_cell(pl + goff[k], G[k][i]);
-                    if (ls.has3) red_cell(pl + goff[3], G[3][i]);
+                        for (int k = 0; k < 3; ++k) red_cell(pl + goff[k], G[k][i]);
+                        if (ls.has3) red_cell(pl + goff[3], G[3][i]);
+                    } else {                               // plane i = half (i & 1) of register i / 2
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const float2 f = unpk2(G[k][i / 2]);
+                            red_cell(pl + goff[k], (i & 1) ? f.y : f.x);
+                        }
+                        if (ls.has3) {
+                            const float2 f = unpk2(G[3][i / 2]);
+                            red_cell(pl + goff[3], (i & 1) ? f.y : f.x);
+                        }
+                    }
                 }
             };
             auto flush_all = [&]() {
@@ -226,16 +268,17 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int i = 0; i < P; ++i) G[k][i] = 0ull;
+                    for (int i = 0; i < NR; ++i) G[k][i] = 0ull;
             };
             auto shift_one = [&]() {                       // next layer: retire 4 planes, slide the other 7 down
                 flush_planes(std::integral_constant<int, 0>{}, std::integral_constant<int, COL>{});
+                constexpr int SH = CPLX ? COL : COL / 2;   // registers per layer
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                    for (int i = 0; i < P - COL; ++i) G[k][i] = G[k][i + COL];
+                    for (int i = 0; i < NR - SH; ++i) G[k][i] = G[k][i + SH];
 #pragma unroll
-                    for (int i = P - COL; i < P; ++i) G[k][i] = 0ull;
+                    for (int i = NR - SH; i < NR; ++i) G[k][i] = 0ull;
                 }
                 ++wl;
             };
@@ -250,7 +293,7 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                 const int k = k0 + bi * BATCH + lane;
                 if (k < k1) {
                     cp_async_stream<16>(st_x, prec + n, pol);   // set_points keeps the folded coordinates in input order
-                    cp_async_stream<8>(st_v, vc + n, pol);
+                    cp_async_stream<(int)sizeof(Cell)>(st_v, vc + n, pol);
                 }
             };
             issue_n(0);
@@ -267,7 +310,8 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                 cp_async_wait0();
                 const float4 xyz = *st_x;
                 const float x = xyz.x, y = xyz.y, z = xyz.z;
-                float2 v = *st_v;
+                float2 v = *st_v;                          // real data: .x only
+                if constexpr (!CPLX) v.y = 0.f;
                 if (nu_weights && lane < nb) wgt = nu_weights[n_cur];
                 n_cur = *st_n;
                 issue_xv(bi + 1, n_cur);
@@ -319,7 +363,7 @@ cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const in
                     PointRec A = load_rec(rec_w + p0 * REC_F, ls);
 #pragma unroll 1
                     for (int p = p0; p < p1; ++p) {
-                        accumulate(G, A);
+                        accumulate<CPLX>(G, A);
                         A = load_rec(rec_w + min(p + 1, p1 - 1) * REC_F, ls);
                     }
                     p0 = p1;

@@ -285,11 +285,11 @@ static bool choose_geometry(Plan &p, bool allow_cs = true)
     g.sub[0] = g.sub[1] = g.sub[2] = 1;
     g.nsub = 1;
 
-    // ---- column-streaming fast path (cs_spread.cuh / cs_interp.cuh): D = 3, M = 4, ComplexF32 -----------------------
+    // ---- column-streaming fast path (cs_spread.cuh / cs_interp.cuh): D = 3, M = 4, Float32 data -----------------------
     // bins = columns of 4 x 4 cells in (x, y), segments of up to 256 cells in z; the sort key is refined by the layer
     // (4 cells in z) inside the segment, so the points of a column arrive bottom to top
     {
-        bool cs = allow_cs && D == 3 && M == 4 && !p.f64 && p.cplx && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
+        bool cs = allow_cs && D == 3 && M == 4 && !p.f64 && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
         if (const char *e = getenv("NUFFT_B200_CS")) cs = cs && atoi(e) != 0;
         for (int d = 0; d < D && cs; ++d)
             if (p.Nos[d] < 16 || p.Nos[d] > 65536 * 4) cs = false;

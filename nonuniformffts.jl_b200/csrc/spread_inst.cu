@@ -30,9 +30,9 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
         PtrPack pack{};
         for (int c = 0; c < cn; ++c) pack.p[c] = vp[c0 + c];
         Cell *us = (Cell *)p.d_us + (int64_t)c0 * p.ncells;
-        if constexpr (std::is_same<T, float>::value && CPLX && D == 3 && M == 4) {
+        if constexpr (std::is_same<T, float>::value && D == 3 && M == 4) {
             if (p.geom.rt == 3 && p.method == NUFFT_METHOD_SHARED_MEMORY) {
-                auto kern = cs::cs_spread_kernel<void>;
+                auto kern = cs::cs_spread_kernel<CPLX>;
                 const size_t smem = cs::spread_smem_bytes(p.cs_stride);
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int nsm = 0;

@@ -207,6 +207,18 @@ def test_column_streaming_sweep(nufft, oracle_mod, monkeypatch, case):
     run_case(nufft, oracle_mod, np.complex64, dims, Np, method="shared_memory", seed=seed, **kw)
 
 
+@pytest.mark.parametrize("case", _sweep_cases(), ids=lambda c: "x".join(map(str, c["dims"])) + f"-{c['Np']}")
+def test_column_streaming_sweep_real_data(nufft, oracle_mod, monkeypatch, case):
+    """Same corner cases with Float32 REAL non-uniform data (r2c plans; the column-streaming kernels keep two z planes per
+    packed register).  fftshift needs complex data (src/plan.jl), so it is dropped from the random draws."""
+    monkeypatch.setenv("NUFFT_B200_CS", "1")
+    monkeypatch.setenv("NUFFT_B200_CS_DENSITY", "0")
+    kw = dict(case)
+    dims, Np, seed = kw.pop("dims"), kw.pop("Np"), kw.pop("seed", 5)
+    kw.pop("fftshift", None)
+    run_case(nufft, oracle_mod, np.float32, dims, Np, method="shared_memory", seed=seed, **kw)
+
+
 JIT_SRC = r"""
 #define NUFFT_HAS_NONUNIFORM 1
 __device__ void nufft_cb_nonuniform(nufft_cell (&v)[NUFFT_C], long long n, const void *user)

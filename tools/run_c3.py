@@ -19,6 +19,7 @@ ap.add_argument("--sigma", type=float, default=2.0)
 ap.add_argument("--method", default="auto")
 ap.add_argument("--dist", default="uniform")
 ap.add_argument("--block", default="")
+ap.add_argument("--real", action="store_true", help="Float32 real non-uniform data (r2c plan) instead of ComplexF32")
 a = ap.parse_args()
 bench.N_MODES = a.modes
 xs, vp, uk = bench.make_inputs(3, a.np)
@@ -28,12 +29,18 @@ if a.dist == "clustered":
 dev = torch.device("cuda", 0)
 xs_d = [torch.from_numpy(x).to(dev) for x in xs]
 vp_d, uk_d = torch.from_numpy(vp).to(dev), torch.from_numpy(uk).to(dev)
-plan = nb.PlanNUFFT(torch.complex64, (a.modes,) * 3, m=a.m, sigma=a.sigma, kernel=nb.BackwardsKaiserBesselKernel(),
+vdt = torch.complex64
+if a.real:
+    vdt = torch.float32
+    vp_d = vp_d.real.contiguous()
+plan = nb.PlanNUFFT(vdt, (a.modes,) * 3, m=a.m, sigma=a.sigma, kernel=nb.BackwardsKaiserBesselKernel(),
                     kernel_evalmode=nb.FastApproximation(), timer=True, gpu_method=a.method,
                     block_size=tuple(int(b) for b in a.block.split(',')) if a.block else None)
 print(repr(plan).splitlines()[-3:])
-out1 = torch.empty((a.modes,) * 3, dtype=torch.complex64, device=dev)
-out2 = torch.empty(a.np, dtype=torch.complex64, device=dev)
+out1 = torch.empty(plan.shape, dtype=torch.complex64, device=dev)
+out2 = torch.empty(a.np, dtype=vdt, device=dev)
+if a.real:
+    uk_d = (torch.randn(out1.shape, device=dev) + 1j * torch.randn(out1.shape, device=dev)).to(torch.complex64)
 for it in range(a.iters):
     plan.set_points(tuple(xs_d))
     plan.exec_type1(out1, vp_d)
