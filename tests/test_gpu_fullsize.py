@@ -157,3 +157,40 @@ def test_c3_kernel_families_agree(nufft, monkeypatch):
         plan.close()
     assert _rel(res["cs"][0], res["tile"][0], torch) <= TOL
     assert _rel(res["cs"][1], res["tile"][1], torch) <= TOL
+
+
+def test_c3_real_data_kernel_families_agree(nufft, monkeypatch):
+    """C3-sized problem with Float32 REAL non-uniform data (r2c plan): column-streaming kernels (two z planes per packed
+    register) vs the generic tiles, and type 1 vs the ComplexF32 plan on the same values (non-negative half of the first
+    Julia dimension, Nyquist mode left out: the real plan keeps +N/2, the complex one -N/2)."""
+    import torch
+    xs, v, _ = _inputs(torch, seed=11)
+    vr = v.real.contiguous()
+    res = {}
+    for family in ("cs", "tile"):
+        monkeypatch.setenv("NUFFT_B200_CS", "1" if family == "cs" else "0")
+        plan = nufft.PlanNUFFT(torch.float32, (N, N, N), m=4, sigma=2.0, kernel=nufft.BackwardsKaiserBesselKernel(),
+                               kernel_evalmode=nufft.FastApproximation())
+        assert tuple(plan.shape) == (N, N, N // 2 + 1)
+        if family == "cs":
+            assert "column-streaming" in repr(plan)
+        plan.set_points(tuple(xs))
+        g = torch.Generator(device="cuda").manual_seed(5)
+        u = torch.complex(torch.randn(plan.shape, generator=g, device="cuda"), torch.randn(plan.shape, generator=g, device="cuda"))
+        o1 = torch.empty(plan.shape, dtype=torch.complex64, device="cuda")
+        o2 = torch.empty(NP, dtype=torch.float32, device="cuda")
+        plan.exec_type1(o1, vr)
+        plan.exec_type2(o2, u)
+        torch.cuda.synchronize()
+        res[family] = (o1, o2)
+        plan.close()
+    assert _rel(res["cs"][0], res["tile"][0], torch) <= TOL
+    assert _rel(res["cs"][1], res["tile"][1], torch) <= TOL
+    monkeypatch.setenv("NUFFT_B200_CS", "1")
+    plan = _plan(nufft, torch)
+    plan.set_points(tuple(xs))
+    oc = torch.empty((N, N, N), dtype=torch.complex64, device="cuda")
+    plan.exec_type1(oc, torch.complex(vr, torch.zeros_like(vr)))
+    torch.cuda.synchronize()
+    plan.close()
+    assert _rel(res["cs"][0][..., : N // 2], oc[..., : N // 2], torch) <= TOL
