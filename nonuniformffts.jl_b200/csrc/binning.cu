@@ -54,53 +54,70 @@ template <> struct PointRec<double> {
 };
 
 // ---- keys --------------------------------------------------------------------------------------
+constexpr int KEYS_ITEMS = 4;
 template <typename T, bool HIST>
 __global__ void __launch_bounds__(256)
 bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
                 uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count, typename PointRec<T>::type *__restrict__ rec)
 {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // KEYS_ITEMS points per thread and iteration: all coordinate loads are issued before the (division-heavy) cell arithmetic,
+    // which keeps enough bytes in flight to cover the HBM latency (one point per thread ran at half the copy bandwidth)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * KEYS_ITEMS;
     const int lane = threadIdx.x & 31;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < np; base += stride) {
-        const int64_t i = base + threadIdx.x;
-        const bool valid = i < np;
-        uint32_t key = 0xffffffffu;
-        if (valid) {
-            T r;
-            T f0 = fold_point<T>(x0[i * g.xstride], g.convention), f1 = (T)0, f2 = (T)0;
-            int c = point_to_cell0<T>(f0, g.N[0], r);
-            int b = c / g.B[0];
-            uint32_t k = (uint32_t)b;
-            int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // refined plans: sub-bins of 4 cells
-            if (g.D > 1) {
-                f1 = fold_point<T>(x1[i * g.xstride], g.convention);
-                c = point_to_cell0<T>(f1, g.N[1], r);
-                b = c / g.B[1];
-                sy = (c - b * g.B[1]) >> 2;
-                k += (uint32_t)b * (uint32_t)g.nb[0];
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x * KEYS_ITEMS; base < np; base += stride) {
+        T xin[KEYS_ITEMS][3];
+#pragma unroll
+        for (int it = 0; it < KEYS_ITEMS; ++it) {
+            const int64_t i = base + (int64_t)it * blockDim.x + threadIdx.x;
+            xin[it][0] = xin[it][1] = xin[it][2] = (T)0;
+            if (i < np) {
+                xin[it][0] = x0[i * g.xstride];
+                if (g.D > 1) xin[it][1] = x1[i * g.xstride];
+                if (g.D > 2) xin[it][2] = x2[i * g.xstride];
             }
-            if (g.D > 2) {
-                f2 = fold_point<T>(x2[i * g.xstride], g.convention);
-                c = point_to_cell0<T>(f2, g.N[2], r);
-                b = c / g.B[2];
-                sz = c - b * g.B[2];
-                sz >>= 2;                                      // layers of 4 cells in z
-                k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
-            }
-            // column-streaming plans: refine by the layer inside the bin (a column of 4 x 4 cells) so that the points of a
-            // column are contiguous and ordered along z; the histogram stays per bin
-            key = k;
-            keys[i] = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
-            // folded coordinates as one 16- / 32-byte record: the gather after the sort then touches one sector per point
-            if (rec) rec[i] = PointRec<T>::make(f0, f1, f2);
         }
-        // warp-aggregated histogram: one atomic per distinct bin in the warp (clustered inputs).  Column-streaming plans
-        // (HIST = false) do not need bin offsets on the path: they are built on demand (binning_ensure_offsets)
-        if (HIST) {
-            const unsigned active = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int it = 0; it < KEYS_ITEMS; ++it) {
+            const int64_t i = base + (int64_t)it * blockDim.x + threadIdx.x;
+            const bool valid = i < np;
+            uint32_t key = 0xffffffffu;
             if (valid) {
-                const unsigned peers = __match_any_sync(active, key);
-                if (lane == __ffs(peers) - 1) atomicAdd(&bin_count[key + 1], (uint32_t)__popc(peers));
+                T r;
+                T f0 = fold_point<T>(xin[it][0], g.convention), f1 = (T)0, f2 = (T)0;
+                int c = point_to_cell0<T>(f0, g.N[0], r);
+                int b = c / g.B[0];
+                uint32_t k = (uint32_t)b;
+                int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // refined plans: sub-bins of 4 cells
+                if (g.D > 1) {
+                    f1 = fold_point<T>(xin[it][1], g.convention);
+                    c = point_to_cell0<T>(f1, g.N[1], r);
+                    b = c / g.B[1];
+                    sy = (c - b * g.B[1]) >> 2;
+                    k += (uint32_t)b * (uint32_t)g.nb[0];
+                }
+                if (g.D > 2) {
+                    f2 = fold_point<T>(xin[it][2], g.convention);
+                    c = point_to_cell0<T>(f2, g.N[2], r);
+                    b = c / g.B[2];
+                    sz = c - b * g.B[2];
+                    sz >>= 2;                                      // layers of 4 cells in z
+                    k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
+                }
+                // column-streaming plans: refine by the layer inside the bin (a column of 4 x 4 cells) so that the points of a
+                // column are contiguous and ordered along z; the histogram stays per bin
+                key = k;
+                keys[i] = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
+                // folded coordinates as one 16- / 32-byte record: the gather after the sort then touches one sector per point
+                if (rec) rec[i] = PointRec<T>::make(f0, f1, f2);
+            }
+            // warp-aggregated histogram: one atomic per distinct bin in the warp (clustered inputs).  Column-streaming plans
+            // (HIST = false) do not need bin offsets on the path: they are built on demand (binning_ensure_offsets)
+            if (HIST) {
+                const unsigned active = __ballot_sync(0xffffffffu, valid);
+                if (valid) {
+                    const unsigned peers = __match_any_sync(active, key);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&bin_count[key + 1], (uint32_t)__popc(peers));
+                }
             }
         }
     }
@@ -432,7 +449,7 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     p.offsets_valid = hist;
     if (hist) CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
     if (np > 0) {
-        const int grid = (int)std::min<int64_t>(cdiv(np, 256), 148 * 16);
+        const int grid = (int)std::min<int64_t>(cdiv(np, 256 * KEYS_ITEMS), 148 * 16);
         auto *rec = p.D > 1 ? (typename PointRec<T>::type *)p.d_rec : nullptr;
         if (hist) bin_keys_kernel<T, true><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec);
         else bin_keys_kernel<T, false><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec);
