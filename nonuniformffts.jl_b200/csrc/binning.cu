@@ -28,6 +28,9 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+#ifndef SCATTER_MIN_CTAS
+#define SCATTER_MIN_CTAS 3      // 85 registers: 3 CTAs (24 warps) per SM instead of 2 at the 113 ptxas picks on its own
+#endif
 static_assert(SORT_THREADS == RADIX, "radix_scatter_kernel: one thread per digit");
 
 struct BinGeom {
@@ -261,7 +264,7 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift, uint3
 // Stable scatter.  Order inside a CTA tile: warp-major, then iteration k, then lane (== index order).  The tile is first
 // reordered by digit in shared memory so that the global writes are runs of consecutive addresses per digit.
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, SCATTER_MIN_CTAS)
 radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
                      const uint32_t *__restrict__ hist_scanned, int nblk,
                      uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out)
