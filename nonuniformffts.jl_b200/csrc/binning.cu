@@ -29,7 +29,7 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 #ifndef SCATTER_MIN_CTAS
-#define SCATTER_MIN_CTAS 3      // 85 registers: 3 CTAs (24 warps) per SM instead of 2 at the 113 ptxas picks on its own
+#define SCATTER_MIN_CTAS 3      // 80 registers: 3 CTAs (24 warps) per SM; ptxas picks 113 (2 CTAs) on its own, 4 CTAs (64 registers, spills) measured slower
 #endif
 static_assert(SORT_THREADS == RADIX, "radix_scatter_kernel: one thread per digit");
 
