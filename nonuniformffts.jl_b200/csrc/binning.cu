@@ -58,16 +58,26 @@ template <> struct PointRec<double> {
 
 // ---- keys --------------------------------------------------------------------------------------
 constexpr int KEYS_ITEMS = 4;
+// The CTA walks whole tiles of the radix sort (SORT_TILE consecutive points) and, when `digit_hist` is given, leaves the
+// histogram of the first radix digit of the tile's keys where radix_hist_kernel would (hist[digit * nblk + tile]): the sort
+// then starts with the scan of its first pass.
 template <typename T, bool HIST>
 __global__ void __launch_bounds__(256)
 bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
-                uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count, typename PointRec<T>::type *__restrict__ rec)
+                uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count, typename PointRec<T>::type *__restrict__ rec,
+                uint32_t *__restrict__ digit_hist, int nblk)
 {
+    static_assert(SORT_TILE % (256 * KEYS_ITEMS) == 0 && SORT_THREADS == 256, "tiles of the sort are walked by whole iterations");
+    __shared__ uint32_t dh[RADIX];
     // KEYS_ITEMS points per thread and iteration: all coordinate loads are issued before the (division-heavy) cell arithmetic,
     // which keeps enough bytes in flight to cover the HBM latency (one point per thread ran at half the copy bandwidth)
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * KEYS_ITEMS;
     const int lane = threadIdx.x & 31;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x * KEYS_ITEMS; base < np; base += stride) {
+    for (int64_t tile = blockIdx.x; tile < nblk; tile += gridDim.x) {
+    if (digit_hist) {
+        dh[threadIdx.x] = 0;
+        __syncthreads();
+    }
+    for (int64_t base = tile * SORT_TILE; base < (tile + 1) * SORT_TILE && base < np; base += 256 * KEYS_ITEMS) {
         T xin[KEYS_ITEMS][3];
 #pragma unroll
         for (int it = 0; it < KEYS_ITEMS; ++it) {
@@ -109,7 +119,9 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
                 // column-streaming plans: refine by the layer inside the bin (a column of 4 x 4 cells) so that the points of a
                 // column are contiguous and ordered along z; the histogram stays per bin
                 key = k;
-                keys[i] = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
+                const uint32_t kfull = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
+                keys[i] = kfull;
+                if (digit_hist) atomicAdd(&dh[kfull & (RADIX - 1)], 1u);
                 // folded coordinates as one 16- / 32-byte record: the gather after the sort then touches one sector per point
                 if (rec) rec[i] = PointRec<T>::make(f0, f1, f2);
             }
@@ -123,6 +135,12 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
                 }
             }
         }
+    }
+    if (digit_hist) {
+        __syncthreads();
+        digit_hist[(size_t)threadIdx.x * nblk + tile] = dh[threadIdx.x];
+        __syncthreads();
+    }
     }
 }
 
@@ -432,7 +450,19 @@ static int ensure_capacity(Plan &p, int64_t np)
     return NUFFT_SUCCESS;
 }
 
-template <typename T> static int set_points_impl(Plan &p, int64_t np, const void *const x[])
+// capacity of the per-tile digit histograms of the radix sort (RADIX counters per tile of SORT_TILE points)
+static int ensure_hist(Plan &p, int64_t np)
+{
+    const size_t hneed = (size_t)cdiv(np, SORT_TILE) * RADIX;
+    if (hneed > p.hist_cap) {
+        if (p.d_hist) cudaFree(p.d_hist);
+        p.hist_cap = hneed + hneed / 8;
+        CUDA_TRY(cudaMalloc(&p.d_hist, p.hist_cap * sizeof(uint32_t)));
+    }
+    return NUFFT_SUCCESS;
+}
+
+template <typename T> static int set_points_impl(Plan &p, int64_t np, const void *const x[], bool first_digit_hist)
 {
     const TileGeom &g = p.geom;
     BinGeom bg;
@@ -452,10 +482,16 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     p.offsets_valid = hist;
     if (hist) CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
     if (np > 0) {
-        const int grid = (int)std::min<int64_t>(cdiv(np, 256 * KEYS_ITEMS), 148 * 16);
+        const int nblk = (int)cdiv(np, SORT_TILE);
+        const int grid = nblk;              // one tile per CTA: the hardware scheduler balances the tail
         auto *rec = p.D > 1 ? (typename PointRec<T>::type *)p.d_rec : nullptr;
-        if (hist) bin_keys_kernel<T, true><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec);
-        else bin_keys_kernel<T, false><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec);
+        uint32_t *dhist = nullptr;
+        if (first_digit_hist) {
+            NUFFT_TRY(ensure_hist(p, np));
+            dhist = p.d_hist;
+        }
+        if (hist) bin_keys_kernel<T, true><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec, dhist, nblk);
+        else bin_keys_kernel<T, false><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec, dhist, nblk);
         NUFFT_COUNT_LAUNCH();
     }
     // slot b+1 holds the count of bin b and slot 0 stays 0: an inclusive scan of this array is exactly
@@ -466,24 +502,22 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
 // stable LSD radix sort of (key, index) pairs restricted to `bits` key bits; the first pass generates the
 // indices.  keys ping-pong between k0/k1 (both clobbered), values between va/vb; *result = final values.
 static int radix_sort_pairs(Plan &p, uint32_t *k0, uint32_t *k1, int32_t *va, int32_t *vb, int64_t np, int bits,
-                            int32_t **result)
+                            int32_t **result, bool first_hist_done = false)
 {
     cudaStream_t st = p.stream;
     const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
     const int nblk = (int)cdiv(np, SORT_TILE);
     const size_t hneed = (size_t)nblk * RADIX;
-    if (hneed > p.hist_cap) {
-        if (p.d_hist) cudaFree(p.d_hist);
-        p.hist_cap = hneed + hneed / 8;
-        CUDA_TRY(cudaMalloc(&p.d_hist, p.hist_cap * sizeof(uint32_t)));
-    }
+    NUFFT_TRY(ensure_hist(p, np));
     uint32_t *kin = k0, *kout = k1;
     int32_t *vin = vb, *vout = va;
     for (int pass = 0; pass < passes; ++pass) {
         const int shift = pass * RADIX_BITS;
         const bool first = pass == 0, last = pass == passes - 1;
-        radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(kin, np, shift, p.d_hist, nblk);
-        NUFFT_COUNT_LAUNCH();
+        if (!(first && first_hist_done)) {           // bin_keys_kernel has left the histogram of the first digit
+            radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(kin, np, shift, p.d_hist, nblk);
+            NUFFT_COUNT_LAUNCH();
+        }
         NUFFT_TRY(scan_u32(p, p.d_hist, (int64_t)hneed, false));
         if (first && last) radix_scatter_kernel<true, true><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
         else if (first) radix_scatter_kernel<true, false><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
@@ -501,7 +535,8 @@ static int radix_sort_pairs(Plan &p, uint32_t *k0, uint32_t *k1, int32_t *va, in
 template <typename T> static int run_set_points(Plan &p, int64_t np, const void *const x[])
 {
     NUFFT_TRY(ensure_capacity(p, np));
-    NUFFT_TRY(set_points_impl<T>(p, np, x));
+    const bool sorts = p.nbins * p.geom.nsub > 1 && np > 0;
+    NUFFT_TRY(set_points_impl<T>(p, np, x, sorts));
     cudaStream_t st = p.stream;
     const int64_t nb1 = p.nbins + 1;
     if (p.offsets_valid) NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_bin_offsets, nb1, true));
@@ -517,7 +552,7 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
         p.sort_cur = 0;
     } else {
         int32_t *res = nullptr;
-        NUFFT_TRY(radix_sort_pairs(p, p.d_keys[0], p.d_keys[1], p.d_vals[1], p.d_vals[0], np, p.key_bits, &res));
+        NUFFT_TRY(radix_sort_pairs(p, p.d_keys[0], p.d_keys[1], p.d_vals[1], p.d_vals[0], np, p.key_bits, &res, true));
         p.d_perm = res;
         p.sort_cur = (res == p.d_vals[0]) ? 0 : 1;
     }
