@@ -131,6 +131,7 @@ __device__ __forceinline__ void red_cell(float *p, float v)
 
 // u64 registers per (x, y) column of the window: complex data one packed (re, im) cell per plane; real data two consecutive
 // planes per register (planes 2j, 2j + 1; the 12th plane is padding and stays zero)
+constexpr int REAL_LAUNCH_BOUND = 640;    // register cap (96) of the real-data spreading kernel, see cs_spread_kernel
 template <bool CPLX> struct Win {
     static constexpr int NR = CPLX ? P : (P + 1) / 2;
 };
@@ -190,7 +191,11 @@ __device__ __forceinline__ void accumulate(u64 (&G)[4][Win<CPLX>::NR], const Poi
 }
 
 template <bool CPLX>                       // complex / real Float32 data (one instantiation per translation unit)
-__global__ void __launch_bounds__(32 * NWARP)       // (no min-blocks hint: with it ptxas renames the accumulators and adds ~30 MOVs per point)
+// (no min-blocks hint: with it ptxas renames the accumulators and adds ~30 MOVs per point.  Real data: with the 168 registers
+//  that 12 warps allow, ptxas writes 18 of the 24 accumulators to fresh registers and copies them back — 48 MOV per point, 38 %
+//  of all instructions in the ncu capture; declaring a bound of 640 threads caps it at 96 registers, the loop is then 24 FFMA2
+//  + 4 FMUL2 + 8 LDS + 4 MOV, no local memory inside it.  The launch still uses 12 warps.)
+__global__ void __launch_bounds__(CPLX ? 32 * NWARP : REAL_LAUNCH_BOUND)
 cs_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
                  const float4 *__restrict__ prec, PtrPack vp, int C,
                  typename CellOf<float, CPLX>::type *__restrict__ us, int64_t ncells, const float *__restrict__ nu_weights)

@@ -2,7 +2,7 @@
 set -x
 K=${1:-cs_spread}
 TAG=${2:-$K}
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s ${3:-1} -c 1 -f -o /tmp/$TAG python tools/run_c3.py --iters 2 > gpurun_out/ncu_$TAG.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s ${3:-1} -c 1 -f -o /tmp/$TAG python tools/run_c3.py --iters 2 ${4:-} > gpurun_out/ncu_$TAG.log 2>&1
 ncu -i /tmp/$TAG.ncu-rep --page details > gpurun_out/${TAG}_details.txt 2>&1
 ncu -i /tmp/$TAG.ncu-rep --page raw --csv > gpurun_out/${TAG}_raw.csv 2>&1
 ncu -i /tmp/$TAG.ncu-rep --page source --csv --print-source cuda,sass > /tmp/${TAG}_src.csv 2>&1
