@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NUFFT_B200_ABI_VERSION 1
+#define NUFFT_B200_ABI_VERSION 2
 
 /* ---- error codes (Julia shim maps them back to the reference's exception types) ---- */
 enum {
@@ -134,9 +134,9 @@ int  nufft_set_points_matrix(nufft_plan plan, int64_t np, const void *xmat);
 int  nufft_get_binning(nufft_plan plan, const int32_t **perm, const int32_t **bin_offsets,
                        int64_t *nbins, int64_t bin_dims[3]);
 
-/* The order the kernels actually use.  Plans on the column-streaming fast path (3-D, ComplexF32, HalfSupport(4), at least
- * one point per 16 fine cells) use bins of 4 x 4 x Bz cells refined into layers of 4 cells along z and sort by
- * key = bin * nsub + layer (stable), a refinement of the reference order; nufft_get_binning then rebuilds the bin-stable
+/* The order the kernels actually use.  Plans on the column-streaming fast path (3-D, Float32 data, HalfSupport(4), at least
+ * one point per 16 fine cells) use bins of 4 x 4 x Bz cells refined by the z cell inside the bin and sort by
+ * key = bin * Bz + z cell (stable), a refinement of the reference order; nufft_get_binning then rebuilds the bin-stable
  * permutation (and the bin offsets) on demand.
  * Other plans: nsub = 1 and both getters agree.  fine_offsets has nfine + 1 entries. */
 int  nufft_get_binning_fine(nufft_plan plan, const int32_t **perm, const int32_t **fine_offsets,
@@ -179,6 +179,57 @@ int  nufft_describe(nufft_plan plan, char *buf, size_t buflen);
 
 const char *nufft_last_error(void);
 int  nufft_abi_version(void);
+
+/* =====================================================================================================================
+ * Multi-GPU transforms (one B200 per rank, NCCL over NVLink / NVSwitch).  The reference has no distributed code
+ * (SURVEY.md §2c); these entry points shard the same hot path — set_points! (src/set_points.jl:33-52),
+ * exec_type1! / exec_type2! (src/NonuniformFFTs.jl:148-291) — the three ways it shards naturally:
+ *   NUFFT_MGPU_SLAB        z-slab spatial decomposition of ONE large transform: points are routed to the rank that owns
+ *                          their z planes, each rank spreads / interpolates on its slab (+ 2M - 1 halo planes exchanged with
+ *                          the two neighbours), the pruned FFT runs its x and y passes on the slab and its z pass after an
+ *                          all-to-all transpose.  3-D, ComplexF32, HalfSupport(4), ntransforms = 1, power-of-two oversampled
+ *                          sizes; oversampled z size and kept y size divisible by the number of ranks.  Uniform data is
+ *                          DISTRIBUTED: rank r holds uhat[:, r Ky/G : (r + 1) Ky/G, :] (nufft_mgpu_local_block).
+ *   NUFFT_MGPU_POINTS      points partitioned, full grid per rank; type 1 sums the partial outputs (all-reduce of
+ *                          prod(size(p)) values), type 2 broadcasts rank 0's coefficients (written into the uhat buffers of
+ *                          the other ranks).  Every plan the single-GPU entry points support.
+ *   NUFFT_MGPU_TRANSFORMS  the C = ntransforms independent transforms are dealt to ranks (c mod nranks == rank): every rank
+ *                          passes the same points and the full tuples of arrays; only its own components are touched.
+ *   NUFFT_MGPU_AUTO        SLAB when eligible, else TRANSFORMS when ntransforms >= nranks, else POINTS.
+ * One handle drives `nlocal` of the `nranks` ranks: nlocal == nranks for a single host process that owns all GPUs (what a
+ * Julia host does through ccall), nlocal == 1 for one process per GPU (the id of nufft_mgpu_unique_id travels through the
+ * host's own channel, e.g. MPI or torch.distributed).  Array arguments are per LOCAL rank l, flattened:
+ * x[3 l + d], vp[C l + c], uhat[C l + c].  All calls are collective over the ranks and stream-ordered on each rank's
+ * stream (nufft_mgpu_get_stream; opts.stream when nlocal == 1).  NCCL is loaded at run time (dlopen of libnccl.so.2).
+ * ===================================================================================================================== */
+#define NUFFT_MGPU_ID_BYTES 128
+enum { NUFFT_MGPU_AUTO = 0, NUFFT_MGPU_SLAB = 1, NUFFT_MGPU_POINTS = 2, NUFFT_MGPU_TRANSFORMS = 3 };
+typedef struct nufft_mgpu_s *nufft_mgpu;
+
+/* ncclGetUniqueId: call on one rank, hand the 128 bytes to every nufft_mgpu_create of the job */
+int  nufft_mgpu_unique_id(void *id128);
+/* PlanNUFFT(...) on every rank (src/plan.jl:467-599); opts.device is ignored (devices[l] is used) */
+int  nufft_mgpu_create(nufft_mgpu *h, const nufft_opts *opts, int32_t nranks, int32_t nlocal, const int32_t *local_ranks,
+                       const int32_t *devices, const void *id128, int32_t strategy);
+int  nufft_mgpu_destroy(nufft_mgpu h);
+/* resolved strategy, rank counts, size(p) and oversampled dims of the GLOBAL problem */
+int  nufft_mgpu_info(nufft_mgpu h, int32_t *strategy, int32_t *nranks, int32_t *nlocal, int64_t size_out[3], int64_t os_dims[3]);
+/* block of the uniform array that local rank l holds: uhat[offset : offset + size) per dimension */
+int  nufft_mgpu_local_block(nufft_mgpu h, int32_t l, int64_t offset[3], int64_t size[3]);
+/* set_points!: local rank l passes ITS np[l] points (any partition of the global set; TRANSFORMS: all points on every rank) */
+int  nufft_mgpu_set_points(nufft_mgpu h, const int64_t np[/*nlocal*/], const void *const x[/*3 nlocal*/]);
+/* exec_type1! / exec_type2!: values belong to the points the same local rank passed to set_points, in the same order */
+int  nufft_mgpu_exec_type1(nufft_mgpu h, void *const uhat[/*C nlocal*/], const void *const vp[/*C nlocal*/], const nufft_callbacks *cb);
+int  nufft_mgpu_exec_type2(nufft_mgpu h, void *const vp[/*C nlocal*/], const void *const uhat[/*C nlocal*/], const nufft_callbacks *cb);
+/* SLAB: all-gather of the distributed type-1 output into a full size(p) array on every local rank (checks, small problems) */
+int  nufft_mgpu_gather_output(nufft_mgpu h, void *const full[/*nlocal*/], const void *const local[/*nlocal*/]);
+int  nufft_mgpu_synchronize(nufft_mgpu h);
+int  nufft_mgpu_get_stream(nufft_mgpu h, int32_t l, void **stream);
+/* per-stage device times (ms) of local rank l, record_timings = 1:  [0] point exchange  [1] local set_points
+ * [2] type-1 value exchange  [3] zero fill + spreading  [4] halo exchange + add  [5] FFT passes x, y  [6] transpose
+ * [7] FFT pass z  [8] type-2 FFT pass z  [9] transpose  [10] FFT passes y, x  [11] halo exchange  [12] interpolation
+ * [13] value return */
+int  nufft_mgpu_get_timings(nufft_mgpu h, int32_t l, float ms[16]);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,8 @@ import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libnufft_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ["NUFFT_B200_LIB"]) if _os.environ.get("NUFFT_B200_LIB") else _HERE / "libnufft_b200.so"
 
 NUFFT_SUCCESS = 0
 NUFFT_ERR_ARG, NUFFT_ERR_DIM, NUFFT_ERR_UNSUPPORTED, NUFFT_ERR_CUDA = -1, -2, -3, -4
@@ -81,7 +82,24 @@ SYMBOLS = {
     "nufft_describe": (C.c_int, [_VP, C.c_char_p, C.c_size_t]),
     "nufft_last_error": (C.c_char_p, []),
     "nufft_abi_version": (C.c_int, []),
+    # multi-GPU transforms (csrc/mgpu.cu)
+    "nufft_mgpu_unique_id": (C.c_int, [_VP]),
+    "nufft_mgpu_create": (C.c_int, [C.POINTER(_VP), C.POINTER(nufft_opts), C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int32), _VP, C.c_int32]),
+    "nufft_mgpu_destroy": (C.c_int, [_VP]),
+    "nufft_mgpu_info": (C.c_int, [_VP, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                  C.POINTER(C.c_int64)]),
+    "nufft_mgpu_local_block": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "nufft_mgpu_set_points": (C.c_int, [_VP, C.POINTER(C.c_int64), _PP]),
+    "nufft_mgpu_exec_type1": (C.c_int, [_VP, _PP, _PP, C.POINTER(nufft_callbacks)]),
+    "nufft_mgpu_exec_type2": (C.c_int, [_VP, _PP, _PP, C.POINTER(nufft_callbacks)]),
+    "nufft_mgpu_gather_output": (C.c_int, [_VP, _PP, _PP]),
+    "nufft_mgpu_synchronize": (C.c_int, [_VP]),
+    "nufft_mgpu_get_stream": (C.c_int, [_VP, C.c_int32, C.POINTER(_VP)]),
+    "nufft_mgpu_get_timings": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_float)]),
 }
+MGPU_STRATEGIES = {"auto": 0, "slab": 1, "points": 2, "transforms": 3}
+MGPU_ID_BYTES = 128
 
 _lib = None
 

@@ -43,6 +43,8 @@ struct BinGeom {
     int rt;          // sub-bin refinement active (TileGeom::rt)
     int sub[3];
     int nsub;
+    int zoff;        // z slab plans: global cell of the slab's first owned plane (0 otherwise)
+    int nzown;       // z cells this plan bins (N[2] unless a slab)
 };
 
 // interleaved record of the folded coordinates of one point (D > 1): float4 / double4
@@ -58,25 +60,27 @@ template <> struct PointRec<double> {
 
 // ---- keys --------------------------------------------------------------------------------------
 constexpr int KEYS_ITEMS = 4;
-// The CTA walks whole tiles of the radix sort (SORT_TILE consecutive points) and, when `digit_hist` is given, leaves the
-// histogram of the first radix digit of the tile's keys where radix_hist_kernel would (hist[digit * nblk + tile]): the sort
-// then starts with the scan of its first pass.
+constexpr int MAX_PASSES = 4;
+// The CTA walks whole tiles of SORT_TILE consecutive points (grid-stride) and, when `ghist` is given, accumulates the digit
+// histograms of ALL radix passes of its keys in shared memory and adds them to ghist[pass][digit] once at the end: the
+// single-sweep sort passes (onesweep_kernel) then need no histogram pass of their own.
 template <typename T, bool HIST>
 __global__ void __launch_bounds__(256)
 bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__restrict__ x1, const T *__restrict__ x2,
                 uint32_t *__restrict__ keys, uint32_t *__restrict__ bin_count, typename PointRec<T>::type *__restrict__ rec,
-                uint32_t *__restrict__ digit_hist, int nblk)
+                uint32_t *__restrict__ ghist, int passes, int nblk)
 {
     static_assert(SORT_TILE % (256 * KEYS_ITEMS) == 0 && SORT_THREADS == 256, "tiles of the sort are walked by whole iterations");
-    __shared__ uint32_t dh[RADIX];
+    __shared__ uint32_t dh[MAX_PASSES][RADIX];
     // KEYS_ITEMS points per thread and iteration: all coordinate loads are issued before the (division-heavy) cell arithmetic,
     // which keeps enough bytes in flight to cover the HBM latency (one point per thread ran at half the copy bandwidth)
     const int lane = threadIdx.x & 31;
-    for (int64_t tile = blockIdx.x; tile < nblk; tile += gridDim.x) {
-    if (digit_hist) {
-        dh[threadIdx.x] = 0;
+    if (ghist) {
+#pragma unroll
+        for (int q = 0; q < MAX_PASSES; ++q) dh[q][threadIdx.x] = 0;
         __syncthreads();
     }
+    for (int64_t tile = blockIdx.x; tile < nblk; tile += gridDim.x) {
     for (int64_t base = tile * SORT_TILE; base < (tile + 1) * SORT_TILE && base < np; base += 256 * KEYS_ITEMS) {
         T xin[KEYS_ITEMS][3];
 #pragma unroll
@@ -100,7 +104,7 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
                 int c = point_to_cell0<T>(f0, g.N[0], r);
                 int b = c / g.B[0];
                 uint32_t k = (uint32_t)b;
-                int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // refined plans: sub-bins of 4 cells
+                int sx = (c - b * g.B[0]) >> 2, sy = 0, sz = 0;   // refined plans: sub-bins of 4 cells in x and y
                 if (g.D > 1) {
                     f1 = fold_point<T>(xin[it][1], g.convention);
                     c = point_to_cell0<T>(f1, g.N[1], r);
@@ -110,18 +114,20 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
                 }
                 if (g.D > 2) {
                     f2 = fold_point<T>(xin[it][2], g.convention);
-                    c = point_to_cell0<T>(f2, g.N[2], r);
+                    c = point_to_cell0<T>(f2, g.N[2], r) - g.zoff;  // z slab plans: cells relative to the slab's first plane
+                    c = c < 0 ? 0 : (c >= g.nzown ? g.nzown - 1 : c);
                     b = c / g.B[2];
-                    sz = c - b * g.B[2];
-                    sz >>= 2;                                      // layers of 4 cells in z
+                    sz = c - b * g.B[2];                           // single cells along z
                     k += (uint32_t)b * (uint32_t)(g.nb[0] * g.nb[1]);
                 }
-                // column-streaming plans: refine by the layer inside the bin (a column of 4 x 4 cells) so that the points of a
+                // column-streaming plans: refine by the z cell inside the bin (a column of 4 x 4 cells) so that the points of a
                 // column are contiguous and ordered along z; the histogram stays per bin
                 key = k;
                 const uint32_t kfull = g.rt ? k * (uint32_t)g.nsub + (uint32_t)((sy * g.sub[0] + sx) * g.sub[2] + sz) : k;
                 keys[i] = kfull;
-                if (digit_hist) atomicAdd(&dh[kfull & (RADIX - 1)], 1u);
+                if (ghist) {
+                    for (int q = 0; q < passes; ++q) atomicAdd(&dh[q][(kfull >> (q * RADIX_BITS)) & (RADIX - 1)], 1u);
+                }
                 // folded coordinates as one 16- / 32-byte record: the gather after the sort then touches one sector per point
                 if (rec) rec[i] = PointRec<T>::make(f0, f1, f2);
             }
@@ -136,11 +142,13 @@ bin_keys_kernel(BinGeom g, int64_t np, const T *__restrict__ x0, const T *__rest
             }
         }
     }
-    if (digit_hist) {
-        __syncthreads();
-        digit_hist[(size_t)threadIdx.x * nblk + tile] = dh[threadIdx.x];
-        __syncthreads();
     }
+    if (ghist) {
+        __syncthreads();
+        for (int q = 0; q < passes; ++q) {
+            const uint32_t v = dh[q][threadIdx.x];
+            if (v) atomicAdd(&ghist[q * RADIX + threadIdx.x], v);
+        }
     }
 }
 
@@ -155,7 +163,9 @@ bin_hist_from_rec_kernel(BinGeom g, int64_t np, const float4 *__restrict__ rec, 
     float t;
     const int b0 = point_to_cell0<float>(r.x, g.N[0], t) / g.B[0];
     const int b1 = point_to_cell0<float>(r.y, g.N[1], t) / g.B[1];
-    const int b2 = point_to_cell0<float>(r.z, g.N[2], t) / g.B[2];
+    int c2 = point_to_cell0<float>(r.z, g.N[2], t) - g.zoff;
+    c2 = c2 < 0 ? 0 : (c2 >= g.nzown ? g.nzown - 1 : c2);
+    const int b2 = c2 / g.B[2];
     atomicAdd(&bin_count[(b2 * g.nb[1] + b1) * g.nb[0] + b0 + 1], 1u);
 }
 
@@ -367,6 +377,140 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__rest
     }
 }
 
+// ---- single-sweep radix passes (decoupled look-back) ----------------------------------------------------------
+// One kernel per digit, no separate histogram / scan launches: bin_keys_kernel has left the global digit histograms of all
+// passes (os_scan_kernel turns them into exclusive digit offsets), and a tile learns the number of equal digits in all
+// EARLIER tiles by looking back through a status array — per (tile, digit) one 32-bit word holding a count and a flag:
+//   00 not ready   01 count of this tile only (aggregate)   10 count of all tiles up to and including this one (inclusive).
+// Tiles are numbered by an atomic ticket taken at CTA start, so every tile a CTA waits for is running or finished.
+// Stability: tile order == index order, and inside a tile the order of radix_scatter_kernel (warp, iteration, lane).
+constexpr uint32_t OS_AGG = 0x40000000u, OS_INC = 0x80000000u, OS_MASK = 0x3fffffffu;
+
+__global__ void __launch_bounds__(RADIX) os_scan_kernel(uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t sm[33];
+    uint32_t *h = ghist + (size_t)blockIdx.x * RADIX;
+    const uint32_t v = h[threadIdx.x];
+    uint32_t total;
+    h[threadIdx.x] = block_exclusive_scan(v, sm, total);
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SORT_THREADS, SCATTER_MIN_CTAS)
+onesweep_kernel(const uint32_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n, int shift,
+                const uint32_t *__restrict__ gbase, uint32_t *__restrict__ status, uint32_t *__restrict__ ticket,
+                uint32_t *__restrict__ keys_out, int32_t *__restrict__ vals_out)
+{
+    __shared__ uint32_t warp_cnt[SORT_WARPS][RADIX];
+    __shared__ uint32_t digit_base[RADIX];       // global position of the first element of (digit, this tile)
+    __shared__ uint32_t local_off[RADIX];        // position of the digit's first element inside the reordered tile
+    __shared__ uint32_t scan_tmp[40];
+    __shared__ uint32_t s_keys[SORT_TILE];
+    __shared__ int32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+
+    const int64_t tbase = (int64_t)tile * SORT_TILE;
+    const int64_t wbase = tbase + (int64_t)warp * (32 * SORT_ITEMS);
+    const int ntile = (int)(n - tbase < SORT_TILE ? n - tbase : SORT_TILE);
+    uint32_t key[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+    int32_t val[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        key[k] = i < n ? keys_in[i] : 0u;
+        val[k] = FIRST ? (int32_t)i : (i < n ? vals_in[i] : 0);
+    }
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t digit = (key[k] >> shift) & (RADIX - 1);
+        const uint32_t tag = valid ? digit : (uint32_t)(RADIX + lane);   // invalid lanes never match anyone
+        const unsigned peers = __match_any_sync(0xffffffffu, tag);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pre = 0;
+        if (lane == leader && valid) {
+            pre = warp_cnt[warp][digit];
+            warp_cnt[warp][digit] = pre + __popc(peers);
+        }
+        pre = __shfl_sync(0xffffffffu, pre, leader);
+        rank[k] = pre + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit (one thread each): exclusive scan over the warps of this tile, tile total, look-back for the global base
+    uint32_t total = 0;
+    {
+        const int d = threadIdx.x;               // SORT_THREADS == RADIX
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t t = warp_cnt[w][d];
+            warp_cnt[w][d] = run;
+            run += t;
+        }
+        total = run;
+        uint32_t *my = status + (size_t)tile * RADIX + d;
+        if (tile == 0) {
+            st_volatile_u32(my, total | OS_INC);
+            digit_base[d] = gbase[d];
+        } else {
+            st_volatile_u32(my, total | OS_AGG);
+            uint32_t excl = 0;
+            for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
+                const uint32_t *ps = status + (size_t)t * RADIX + d;
+                uint32_t v;
+                do { v = ld_volatile_u32(ps); } while ((v & (OS_AGG | OS_INC)) == 0);
+                excl += v & OS_MASK;
+                if (v & OS_INC) break;
+            }
+            st_volatile_u32(my, (excl + total) | OS_INC);
+            digit_base[d] = gbase[d] + excl;
+        }
+    }
+    {
+        uint32_t sum;
+        const uint32_t ex = block_exclusive_scan(total, scan_tmp, sum);
+        local_off[threadIdx.x] = ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (key[k] >> shift) & (RADIX - 1);
+            const uint32_t lpos = local_off[digit] + warp_cnt[warp][digit] + rank[k];
+            s_keys[lpos] = key[k];
+            s_vals[lpos] = val[k];
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ntile; t += SORT_THREADS) {
+        const uint32_t kk = s_keys[t];
+        const uint32_t digit = (kk >> shift) & (RADIX - 1);
+        const uint32_t pos = digit_base[digit] + ((uint32_t)t - local_off[digit]);
+        if (!LAST) keys_out[pos] = kk;
+        vals_out[pos] = s_vals[t];
+    }
+}
+
 // ---- sorted, folded copy of the points ---------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -462,7 +606,23 @@ static int ensure_hist(Plan &p, int64_t np)
     return NUFFT_SUCCESS;
 }
 
-template <typename T> static int set_points_impl(Plan &p, int64_t np, const void *const x[], bool first_digit_hist)
+// scratch of the single-sweep sort: [MAX_PASSES][RADIX] global digit histograms | [MAX_PASSES] tile tickets (padded to RADIX
+// words) | [passes][nblk][RADIX] look-back status words; zeroed by one memset per set_points
+static int ensure_onesweep(Plan &p, int64_t np, int passes, size_t *bytes)
+{
+    const size_t need = ((size_t)(MAX_PASSES + 1) * RADIX + (size_t)passes * cdiv(np, SORT_TILE) * RADIX) * sizeof(uint32_t);
+    if (need > p.os_cap) {
+        if (p.d_os) cudaFree(p.d_os);
+        p.d_os = nullptr;
+        p.os_cap = 0;
+        CUDA_TRY(cudaMalloc(&p.d_os, need + need / 8));
+        p.os_cap = need + need / 8;
+    }
+    *bytes = need;
+    return NUFFT_SUCCESS;
+}
+
+template <typename T> static int set_points_impl(Plan &p, int64_t np, const void *const x[], int os_passes)
 {
     const TileGeom &g = p.geom;
     BinGeom bg;
@@ -472,6 +632,8 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     for (int d = 0; d < 3; ++d) { bg.N[d] = g.N[d]; bg.B[d] = g.B[d]; bg.nb[d] = g.nb[d]; bg.sub[d] = g.sub[d]; }
     bg.rt = g.rt;
     bg.nsub = g.nsub;
+    bg.zoff = p.slab_z0;
+    bg.nzown = p.slab_nz > 0 ? p.slab_nz : g.N[2];
     const T *x0 = (const T *)x[0];
     const T *x1 = p.D > 1 ? (const T *)x[1] : nullptr;
     const T *x2 = p.D > 2 ? (const T *)x[2] : nullptr;
@@ -483,15 +645,17 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     if (hist) CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), st));
     if (np > 0) {
         const int nblk = (int)cdiv(np, SORT_TILE);
-        const int grid = nblk;              // one tile per CTA: the hardware scheduler balances the tail
+        const int grid = std::min(nblk, p.num_sms * 8);       // persistent CTAs: few global histogram atomics
         auto *rec = p.D > 1 ? (typename PointRec<T>::type *)p.d_rec : nullptr;
-        uint32_t *dhist = nullptr;
-        if (first_digit_hist) {
-            NUFFT_TRY(ensure_hist(p, np));
-            dhist = p.d_hist;
+        uint32_t *ghist = nullptr;
+        if (os_passes > 0) {
+            size_t bytes = 0;
+            NUFFT_TRY(ensure_onesweep(p, np, os_passes, &bytes));
+            CUDA_TRY(cudaMemsetAsync(p.d_os, 0, bytes, st));
+            ghist = p.d_os;
         }
-        if (hist) bin_keys_kernel<T, true><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec, dhist, nblk);
-        else bin_keys_kernel<T, false><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec, dhist, nblk);
+        if (hist) bin_keys_kernel<T, true><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec, ghist, os_passes, nblk);
+        else bin_keys_kernel<T, false><<<grid, 256, 0, st>>>(bg, np, x0, x1, x2, p.d_keys[0], bin_count, rec, ghist, os_passes, nblk);
         NUFFT_COUNT_LAUNCH();
     }
     // slot b+1 holds the count of bin b and slot 0 stays 0: an inclusive scan of this array is exactly
@@ -499,10 +663,39 @@ template <typename T> static int set_points_impl(Plan &p, int64_t np, const void
     return NUFFT_SUCCESS;
 }
 
+// stable LSD radix sort of (key, index) pairs, one kernel per digit (see onesweep_kernel); the digit histograms of all
+// passes are in p.d_os (bin_keys_kernel).  Same result as radix_sort_pairs.
+static int onesweep_sort_pairs(Plan &p, uint32_t *k0, uint32_t *k1, int32_t *va, int32_t *vb, int64_t np, int passes, int32_t **result)
+{
+    cudaStream_t st = p.stream;
+    const int nblk = (int)cdiv(np, SORT_TILE);
+    uint32_t *ghist = p.d_os, *tickets = p.d_os + MAX_PASSES * RADIX, *status = p.d_os + (MAX_PASSES + 1) * RADIX;
+    os_scan_kernel<<<passes, RADIX, 0, st>>>(ghist);
+    NUFFT_COUNT_LAUNCH();
+    uint32_t *kin = k0, *kout = k1;
+    int32_t *vin = vb, *vout = va;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = pass * RADIX_BITS;
+        const bool first = pass == 0, last = pass == passes - 1;
+        const uint32_t *gb = ghist + pass * RADIX;
+        uint32_t *stt = status + (size_t)pass * nblk * RADIX, *tk = tickets + pass;
+        if (first && last) onesweep_kernel<true, true><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, gb, stt, tk, kout, vout);
+        else if (first) onesweep_kernel<true, false><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, gb, stt, tk, kout, vout);
+        else if (last) onesweep_kernel<false, true><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, gb, stt, tk, kout, vout);
+        else onesweep_kernel<false, false><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, gb, stt, tk, kout, vout);
+        NUFFT_COUNT_LAUNCH();
+        std::swap(kin, kout);
+        *result = vout;
+        std::swap(vin, vout);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return NUFFT_SUCCESS;
+}
+
 // stable LSD radix sort of (key, index) pairs restricted to `bits` key bits; the first pass generates the
 // indices.  keys ping-pong between k0/k1 (both clobbered), values between va/vb; *result = final values.
 static int radix_sort_pairs(Plan &p, uint32_t *k0, uint32_t *k1, int32_t *va, int32_t *vb, int64_t np, int bits,
-                            int32_t **result, bool first_hist_done = false)
+                            int32_t **result)
 {
     cudaStream_t st = p.stream;
     const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
@@ -514,10 +707,8 @@ static int radix_sort_pairs(Plan &p, uint32_t *k0, uint32_t *k1, int32_t *va, in
     for (int pass = 0; pass < passes; ++pass) {
         const int shift = pass * RADIX_BITS;
         const bool first = pass == 0, last = pass == passes - 1;
-        if (!(first && first_hist_done)) {           // bin_keys_kernel has left the histogram of the first digit
-            radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(kin, np, shift, p.d_hist, nblk);
-            NUFFT_COUNT_LAUNCH();
-        }
+        radix_hist_kernel<<<nblk, SORT_THREADS, 0, st>>>(kin, np, shift, p.d_hist, nblk);
+        NUFFT_COUNT_LAUNCH();
         NUFFT_TRY(scan_u32(p, p.d_hist, (int64_t)hneed, false));
         if (first && last) radix_scatter_kernel<true, true><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
         else if (first) radix_scatter_kernel<true, false><<<nblk, SORT_THREADS, 0, st>>>(kin, vin, np, shift, p.d_hist, nblk, kout, vout);
@@ -534,16 +725,21 @@ static int radix_sort_pairs(Plan &p, uint32_t *k0, uint32_t *k1, int32_t *va, in
 
 template <typename T> static int run_set_points(Plan &p, int64_t np, const void *const x[])
 {
+    p.Np = -1;                              // a failure below leaves the plan without points (exec then reports NUFFT_ERR_STATE)
     NUFFT_TRY(ensure_capacity(p, np));
     const bool sorts = p.nbins * p.geom.nsub > 1 && np > 0;
-    NUFFT_TRY(set_points_impl<T>(p, np, x, sorts));
+    const int passes = (p.key_bits + RADIX_BITS - 1) / RADIX_BITS;
+    // single-sweep passes: counts and prefixes share a 30-bit field of the status words
+    bool onesweep = sorts && passes <= MAX_PASSES && np < ((int64_t)1 << 30);
+    if (const char *e = getenv("NUFFT_B200_ONESWEEP")) onesweep = onesweep && atoi(e) != 0;
+    NUFFT_TRY(set_points_impl<T>(p, np, x, onesweep ? passes : 0));
     cudaStream_t st = p.stream;
     const int64_t nb1 = p.nbins + 1;
     if (p.offsets_valid) NUFFT_TRY(scan_u32(p, (uint32_t *)p.d_bin_offsets, nb1, true));
     p.perm_coarse_ptr = nullptr;
 
     // stable LSD radix sort of (key, index)
-    if (p.nbins * p.geom.nsub <= 1 || np == 0) {
+    if (!sorts) {
         if (np > 0) {
             iota_kernel<<<(unsigned)cdiv(np, 256), 256, 0, st>>>(p.d_vals[0], np);
             NUFFT_COUNT_LAUNCH();
@@ -552,7 +748,8 @@ template <typename T> static int run_set_points(Plan &p, int64_t np, const void 
         p.sort_cur = 0;
     } else {
         int32_t *res = nullptr;
-        NUFFT_TRY(radix_sort_pairs(p, p.d_keys[0], p.d_keys[1], p.d_vals[1], p.d_vals[0], np, p.key_bits, &res, true));
+        if (onesweep) NUFFT_TRY(onesweep_sort_pairs(p, p.d_keys[0], p.d_keys[1], p.d_vals[1], p.d_vals[0], np, passes, &res));
+        else NUFFT_TRY(radix_sort_pairs(p, p.d_keys[0], p.d_keys[1], p.d_vals[1], p.d_vals[0], np, p.key_bits, &res));
         p.d_perm = res;
         p.sort_cur = (res == p.d_vals[0]) ? 0 : 1;
     }
@@ -596,6 +793,8 @@ int binning_ensure_offsets(Plan &p)
     BinGeom bg{};
     bg.D = p.D;
     for (int d = 0; d < 3; ++d) { bg.N[d] = g.N[d]; bg.B[d] = g.B[d]; bg.nb[d] = g.nb[d]; }
+    bg.zoff = p.slab_z0;
+    bg.nzown = p.slab_nz > 0 ? p.slab_nz : g.N[2];
     uint32_t *bin_count = (uint32_t *)p.d_bin_offsets;
     CUDA_TRY(cudaMemsetAsync(bin_count, 0, (size_t)(p.nbins + 1) * sizeof(uint32_t), p.stream));
     if (p.Np > 0) {

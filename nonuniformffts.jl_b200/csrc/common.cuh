@@ -206,6 +206,15 @@ struct Plan {
     int2 *d_item_table = nullptr;    // per work item: (bin, chunk index)
     size_t item_cap = 0;
     int32_t *d_counters = nullptr;   // small block of device counters
+    uint32_t *d_os = nullptr;        // single-sweep sort scratch: digit histograms, tile tickets, look-back status (binning.cu)
+    size_t os_cap = 0;               // bytes
+    int num_sms = 148;
+
+    // z-slab plans (multi-GPU, mgpu.cu): the plan's grid holds the planes slab_z0 - (M - 1) .. slab_z0 + slab_nz + M - 1 of the
+    // global oversampled grid (owned planes + halo), no periodic wrap along z; points must lie in the owned planes.
+    int slab_z0 = 0;                 // first owned plane (global index)
+    int slab_nz = 0;                 // owned planes; 0 = not a slab plan (full periodic grid)
+    int nz_local = 0;                // planes stored (= Nos[2] for a full grid, slab_nz + 2M - 1 for a slab)
 
     // timings
     cudaEvent_t ev[32] = {};

@@ -286,23 +286,25 @@ static bool choose_geometry(Plan &p, bool allow_cs = true)
     g.nsub = 1;
 
     // ---- column-streaming fast path (cs_spread.cuh / cs_interp.cuh): D = 3, M = 4, Float32 data -----------------------
-    // bins = columns of 4 x 4 cells in (x, y), segments of up to 256 cells in z; the sort key is refined by the layer
-    // (4 cells in z) inside the segment, so the points of a column arrive bottom to top
+    // bins = columns of 4 x 4 cells in (x, y), segments of up to 256 cells in z; the sort key is refined by the z cell
+    // inside the segment, so the points of a column arrive bottom to top, cell by cell
     {
         bool cs = allow_cs && D == 3 && M == 4 && !p.f64 && p.opts.gpu_method != NUFFT_METHOD_GLOBAL_MEMORY && !user;
         if (const char *e = getenv("NUFFT_B200_CS")) cs = cs && atoi(e) != 0;
         for (int d = 0; d < D && cs; ++d)
             if (p.Nos[d] < 16 || p.Nos[d] > 65536 * 4) cs = false;
-        if (p.Nos[0] * p.Nos[1] * p.Nos[2] >= ((int64_t)1 << 31)) cs = false;        // 32-bit cell offsets
+        if (p.ncells >= ((int64_t)1 << 31)) cs = false;        // 32-bit cell offsets
         if (cs) {
             g.rt = 3;
-            int Bc[3] = {4, 4, (int)std::min<int64_t>(256, bcap(2)) / 4 * 4};
+            // (a z slab bins its owned planes only)
+            const int64_t nzown = p.slab_nz > 0 ? p.slab_nz : p.Nos[2];
+            int Bc[3] = {4, 4, (int)std::max<int64_t>(4, std::min<int64_t>(256, p.slab_nz > 0 ? nzown : bcap(2)) / 4 * 4)};
             tile_bytes(Bc, T, S);               // strides of the generic shared-memory kernels (unused on this path)
             int64_t nbins = 1;
             for (int d = 0; d < 3; ++d) {
                 g.B[d] = Bc[d]; g.T[d] = T[d]; g.S[d] = S[d];
-                g.sub[d] = d < 2 ? 1 : Bc[2] / 4;
-                g.nb[d] = (int)cdiv(p.Nos[d], Bc[d]);
+                g.sub[d] = d < 2 ? 1 : Bc[2];          // the sort key is refined by the z CELL inside the segment
+                g.nb[d] = (int)cdiv(d == 2 ? nzown : p.Nos[d], Bc[d]);
                 nbins *= g.nb[d];
             }
             g.nsub = g.sub[2];
@@ -394,6 +396,7 @@ int host_plan_init(Plan &p)
     p.stream = (cudaStream_t)o.stream;
     if (o.device >= 0) { CUDA_TRY(cudaSetDevice(o.device)); }
     CUDA_TRY(cudaGetDevice(&p.device));
+    CUDA_TRY(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, p.device));
 
     // oversampled sizes (sigma converted to T first, src/plan.jl:575-576)
     for (int d = 0; d < p.D; ++d) {
@@ -417,7 +420,15 @@ int host_plan_init(Plan &p)
         p.Nspec[d] = half ? Nt / 2 + 1 : Nt;
         p.nk[d] = half ? N / 2 + 1 : N;
     }
-    p.ncells = p.Nos[0] * p.Nos[1] * p.Nos[2];
+    p.nz_local = (int)p.Nos[2];
+    if (p.slab_nz > 0) {
+        if (p.D != 3 || p.slab_z0 < 0 || p.slab_z0 + p.slab_nz > p.Nos[2] || p.slab_nz < p.M) {
+            set_error("invalid z slab [%d, %d) of %lld planes", p.slab_z0, p.slab_z0 + p.slab_nz, (long long)p.Nos[2]);
+            return NUFFT_ERR_ARG;
+        }
+        p.nz_local = p.slab_nz + 2 * p.M - 1;
+    }
+    p.ncells = p.Nos[0] * p.Nos[1] * (int64_t)p.nz_local;
     p.nspec = p.Nspec[0] * p.Nspec[1] * p.Nspec[2];
     p.nkept = p.nk[0] * p.nk[1] * p.nk[2];
     if (p.ncells >= ((int64_t)1 << 31)) { set_error("oversampled grid has >= 2^31 cells (32-bit cell indices)"); return NUFFT_ERR_UNSUPPORTED; }
@@ -438,7 +449,13 @@ int host_plan_init(Plan &p)
 
     // bins / tiles and method
     bool sm_ok = choose_geometry(p);
-    if (p.geom.rt == 3) {
+    if (p.slab_nz > 0 && p.geom.rt != 3) {
+        set_error("z-slab plans need the column-streaming kernels (3-D, HalfSupport(4), Float32)");
+        return NUFFT_ERR_UNSUPPORTED;
+    }
+    if (p.geom.rt == 3 && p.slab_nz > 0) {
+        sm_ok = true;
+    } else if (p.geom.rt == 3) {
         // keep the tile geometry too: set_points picks by density (NUFFT_B200_CS_DENSITY = cells per point below which the
         // column-streaming kernels are used; 0 = always)
         p.geom_alt[0] = p.geom; p.nbins_alt[0] = p.nbins; p.key_bits_alt[0] = p.key_bits;
@@ -474,6 +491,7 @@ int host_plan_init(Plan &p)
 
     // pruned FFT fused with deconvolution (pfft.cu) when the plan is eligible; cuFFT + K-deconv otherwise
     p.pfft = pfft_eligible(p);
+    if (p.slab_nz > 0 && !p.pfft) { set_error("z-slab plans need the pruned FFT (complex data, power-of-two oversampled sizes)"); return NUFFT_ERR_UNSUPPORTED; }
     if (p.pfft) NUFFT_TRY(pfft_init(p));
 
     // cuFFT plans: Julia dims are column-major -> reversed for cuFFT; batch = ntransforms
@@ -534,6 +552,7 @@ void host_plan_free(Plan &p)
     for (int d = 0; d < 3; ++d) { f(p.d_phihat[d]); f(p.d_imap[d]); f(p.d_invmap[d]); f(p.d_xs[d]); }
     f(p.d_keys[0]); f(p.d_keys[1]); f(p.d_vals[0]); f(p.d_vals[1]); f(p.d_rec);
     f(p.d_perm_coarse);
+    f(p.d_os);
     f(p.d_bin_offsets); f(p.d_hist); f(p.d_scan_tmp); f(p.d_item_start); f(p.d_item_table); f(p.d_counters);
     if (p.ev_ok) { for (int i = 0; i < 32; ++i) cudaEventDestroy(p.ev[i]); p.ev_ok = false; }
 }

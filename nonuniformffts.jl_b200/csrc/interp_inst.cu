@@ -5,6 +5,7 @@
 #include <type_traits>
 #include "interp.cuh"
 #include "cs_interp.cuh"
+#include "ring_interp.cuh"
 
 #ifndef INST_T
 #define INST_T float
@@ -34,13 +35,34 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
         const Cell *us = (const Cell *)p.d_us + (int64_t)c0 * p.ncells;
         if constexpr (std::is_same<T, float>::value && D == 3 && M == 4) {
             if (p.geom.rt == 3 && p.method == NUFFT_METHOD_SHARED_MEMORY) {
+                const int zlo = p.slab_nz > 0 ? p.slab_z0 - (M - 1) : 0, nzwrap = p.slab_nz > 0 ? (1 << 30) : (int)p.Nos[2];
+                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
+                static bool ring_off = getenv("NUFFT_B200_RING") && atoi(getenv("NUFFT_B200_RING")) == 0;
+                if constexpr (CPLX) {
+                    if (!ring_off) {
+                        auto kern = ring::ring_interp_kernel<ring::NWARP>;
+                        const size_t smem = ring::interp_smem_bytes(p.cs_stride);
+                        static bool attr_done = false;
+                        if (!attr_done) {
+                            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            attr_done = true;
+                        }
+                        kern<<<p.num_sms, 32 * ring::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters,
+                                                                        (const float4 *)p.d_rec, pack, cn, us, p.ncells, prefactor, nuw, zlo, nzwrap,
+                                                                        p.nz_local);
+                        NUFFT_COUNT_LAUNCH();
+                        continue;
+                    }
+                }
+                if (p.slab_nz > 0) { set_error("z-slab plans need the ring kernels (complex data)"); return NUFFT_ERR_UNSUPPORTED; }
                 auto kern = cs::cs_interp_kernel<CPLX>;
                 const size_t smem = cs::interp_smem_bytes(p.cs_stride);
-                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int nsm = 0;
-                CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
-                CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
-                kern<<<nsm, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters, (const float4 *)p.d_rec, pack, cn, us,
+                static bool attr_done = false;
+                if (!attr_done) {
+                    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    attr_done = true;
+                }
+                kern<<<p.num_sms, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters, (const float4 *)p.d_rec, pack, cn, us,
                                                         p.ncells, prefactor, nuw);
                 NUFFT_COUNT_LAUNCH();
                 continue;
@@ -53,10 +75,14 @@ static int interp_launch(Plan &p, void *const vp[], const nufft_callbacks *cb)
         } else {
             auto kern = interp_sm_kernel<T, CPLX, D, M>;
             const size_t smem = sm_dynamic_bytes<T, CPLX, D, M, false>(p.geom, p.cs_stride);
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int occ = 0, nsm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, INTERP_THREADS, smem));
-            CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+            static size_t smem_set = 0;                        // per instantiation: attribute / occupancy queried once per size
+            static int occ = 0;
+            if (smem_set != smem + 1) {
+                CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, INTERP_THREADS, smem));
+                smem_set = smem + 1;
+            }
+            const int nsm = p.num_sms;
             if (occ < 1) { set_error("interp_sm_kernel cannot be resident (smem %zu bytes)", smem); return NUFFT_ERR_UNSUPPORTED; }
             SmArgs a{p.d_perm, p.d_bin_offsets, p.d_item_start, p.d_item_table, p.d_counters, (int)p.nbins};
             CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));

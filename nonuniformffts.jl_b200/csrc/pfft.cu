@@ -41,6 +41,11 @@ template <typename T> struct PfftArgs {
     int K0, K1;            // kept sizes of the faster dimensions (to split `lo` for the separable factors)
     const T *fsep[3];
     const T *fdense;
+    // strided passes of the z-slab pipeline (mgpu.cu): the kept side is split into blocks of `blk` kept indices, one per
+    // destination rank of the transpose that follows / source rank of the one that preceded: element (lo, I, hi) lives at
+    // lo + n_lo ((I % blk) + blk hi) + (I / blk) blk_stride.  blk = 0: plain layout lo + n_lo (I + K hi).
+    int blk;
+    int64_t blk_stride;
 };
 
 template <typename T> __host__ __device__ constexpr int pf_group() { return 128 / (2 * (int)sizeof(T)); }
@@ -293,6 +298,11 @@ __global__ void __launch_bounds__(pf_nt<T>(L), 4) pfft_pass_kernel(PfftArgs<T> a
     const int64_t full_step = CONTIG ? (int64_t)NT : a.n_lo * (NT / TW);
     // kept elements of this thread: CONTIG: e = tid + n NT over the contiguous block of TW x K; strided: as above with K
     const int64_t kept_base = CONTIG ? (int64_t)K * hi0 + tid : lo0 + tid % TW + a.n_lo * (tid / TW + (int64_t)K * hi0);
+    auto kept_off = [&](int I, int n) -> int64_t {       // offset of kept element I (= tid / TW + n NT / TW in strided passes)
+        if (CONTIG || a.blk == 0) return kept_base + n * full_step;
+        const int b = I / a.blk;
+        return lo0 + tid % TW + a.n_lo * ((int64_t)(I - b * a.blk) + (int64_t)a.blk * hi0) + (int64_t)b * a.blk_stride;
+    };
 
     // ---- load (all global loads of a thread are issued before the first shared-memory store) ------------------------
     if constexpr (FWD) {
@@ -319,7 +329,7 @@ __global__ void __launch_bounds__(pf_nt<T>(L), 4) pfft_pass_kernel(PfftArgs<T> a
         for (int n = 0; n < EPT; ++n) {
             pos[n] = -1;
             if (line < nlines && I < K) {
-                const C2 v = a.in[kept_base + n * full_step];
+                const C2 v = a.in[kept_off(I, n)];
                 const T f = factor(line, I);
                 r[n].x = v.x * f; r[n].y = -(v.y * f);
                 pos[n] = pf_slot<T, L>(line, pf_phys<T>(a.imap[I]));
@@ -339,7 +349,6 @@ __global__ void __launch_bounds__(pf_nt<T>(L), 4) pfft_pass_kernel(PfftArgs<T> a
     if constexpr (FWD) {
         // rolled loop: K <= L kept modes per line, so up to half of the EPT slots of a thread are empty
         int line = CONTIG ? tid / K : tid % TW, I = CONTIG ? tid % K : tid / TW;
-        C2 *dst = a.out + kept_base;
 #pragma unroll 4
         for (int n = 0; n < EPT; ++n) {
             if (CONTIG ? line >= nlines : I >= K) break;
@@ -347,9 +356,8 @@ __global__ void __launch_bounds__(pf_nt<T>(L), 4) pfft_pass_kernel(PfftArgs<T> a
                 C2 v = s[pf_slot<T, L>(line, pf_phys<T>(a.imap[I]))];
                 const T f = factor(line, I);
                 v.x *= f; v.y *= f;
-                *dst = v;
+                a.out[kept_off(I, n)] = v;
             }
-            dst += full_step;
             if constexpr (CONTIG) { I += NT; while (I >= K) { I -= K; ++line; } }
             else I += NT / TW;
         }
@@ -459,7 +467,7 @@ template <typename T> static int pfft_init_t(Plan &p)
     // scratch A: [K0][N1][N2] (3-D) or [K0][N1] (2-D); the second 3-D intermediate [K0][K1][N2] lives in the grid itself
     size_t na = 0;
     if (p.D == 2) na = (size_t)p.nk[0] * p.Nos[1];
-    if (p.D == 3) na = (size_t)p.nk[0] * p.Nos[1] * p.Nos[2];
+    if (p.D == 3) na = (size_t)p.nk[0] * p.Nos[1] * (p.slab_nz > 0 ? p.slab_nz : p.Nos[2]);
     if (na) CUDA_TRY(cudaMalloc(&p.d_pf_a, na * sizeof(C2)));
     return NUFFT_SUCCESS;
 }
@@ -543,6 +551,32 @@ template <typename T> static int pfft_type2_t(Plan &p, const void *const uhat[],
     }
     CUDA_TRY(cudaGetLastError());
     return NUFFT_SUCCESS;
+}
+
+// one pruned pass along dimension d over an array with n_lo faster / n_hi slower elements (z-slab pipeline, mgpu.cu)
+template <typename T>
+static int pfft_pass_t(Plan &p, int d, bool fwd, const void *in, void *out, int64_t n_lo, int64_t n_hi, double scale, int blk,
+                       int64_t blk_stride)
+{
+    using C2 = typename Vec2<T>::type;
+    PfftArgs<T> a = pf_args<T>(p, d, nullptr, false);
+    a.in = (const C2 *)in;
+    a.out = (C2 *)out;
+    a.n_lo = n_lo;
+    a.n_hi = n_hi;
+    a.scale = (T)scale;
+    a.blk = blk;
+    a.blk_stride = blk_stride;
+    if (fwd) NUFFT_TRY((pf_launch<T, true>((int)p.Nos[d], a, p.stream)));
+    else NUFFT_TRY((pf_launch<T, false>((int)p.Nos[d], a, p.stream)));
+    CUDA_TRY(cudaGetLastError());
+    return NUFFT_SUCCESS;
+}
+
+int pfft_pass(Plan &p, int d, bool fwd, const void *in, void *out, int64_t n_lo, int64_t n_hi, double scale, int blk, int64_t blk_stride)
+{
+    return p.f64 ? pfft_pass_t<double>(p, d, fwd, in, out, n_lo, n_hi, scale, blk, blk_stride)
+                 : pfft_pass_t<float>(p, d, fwd, in, out, n_lo, n_hi, scale, blk, blk_stride);
 }
 
 int pfft_type1_run(Plan &p, void *const uhat[], const nufft_callbacks *cb)

@@ -135,6 +135,43 @@ def _to_torch_dtype(dt) -> torch.dtype:
     return m[np.dtype(dt)]
 
 
+def build_opts(lib, dims, is_complex, real_dtype, M, sigma, kernel, mode_name, ntransforms, fftshift, sort_points, gpu_method,
+               block_size, point_convention, device_index, stream, timer, spread_chunk) -> nufft_opts:
+    """nufft_opts of a plan = the keyword arguments of PlanNUFFT (src/plan.jl:467-599)."""
+    o = nufft_opts()
+    _check(lib.nufft_opts_default(C.byref(o)))
+    o.dim = len(dims)
+    for d, n in enumerate(dims):
+        o.n_modes[d] = n
+    o.is_complex = 1 if is_complex else 0
+    o.dtype = _lib.NUFFT_F64 if real_dtype == torch.float64 else _lib.NUFFT_F32
+    o.half_support = M
+    o.sigma = float(sigma)
+    o.kernel = _lib.KERNEL_IDS[kernel.name]
+    o.kernel_param = float("nan") if kernel.param is None else float(kernel.param)
+    o.eval_mode = _lib.EVAL_IDS[mode_name]
+    o.ntransforms = int(ntransforms)
+    o.fftshift = 1 if fftshift else 0
+    o.sort_points = 1 if sort_points else 0
+    o.gpu_method = _lib.METHOD_IDS[gpu_method]
+    if block_size is not None:
+        if isinstance(block_size, int):
+            # the reference turns a linear block size into power-of-two block dims (src/plan.jl:437-449) for its CPU path and
+            # ignores it in the GPU shared-memory method (src/plan.jl:216,236-238); this backend sizes its bins itself
+            if block_size < 1:
+                raise ArgumentError("block_size must be positive")
+        else:
+            for d, b in enumerate(block_size):
+                o.block_dims[d] = int(b)
+    o.point_convention = int(point_convention)
+    o.device = -1 if device_index is None else int(device_index)
+    if stream is not None:
+        o.stream = C.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
+    o.record_timings = 1 if timer else 0
+    o.spread_chunk = int(spread_chunk)
+    return o
+
+
 class PlanNUFFT:
     """PlanNUFFT([T = ComplexF64], dims; m = 4, sigma = 2, kernel, ntransforms = 1, fftshift = false, ...).
 
@@ -180,33 +217,11 @@ class PlanNUFFT:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
 
-        o = nufft_opts()
-        _check(self._lib.nufft_opts_default(C.byref(o)))
-        o.dim = len(dims)
-        for d, n in enumerate(dims):
-            o.n_modes[d] = n
-        o.is_complex = 1 if self.is_complex else 0
-        o.dtype = _lib.NUFFT_F64 if self.real_dtype == torch.float64 else _lib.NUFFT_F32
-        o.half_support = M
-        o.sigma = float(sigma)
-        o.kernel = _lib.KERNEL_IDS[kernel.name]
-        o.kernel_param = float("nan") if kernel.param is None else float(kernel.param)
-        o.eval_mode = _lib.EVAL_IDS[mode_name]
-        o.ntransforms = int(ntransforms)
-        o.fftshift = 1 if fftshift else 0
-        o.sort_points = 1 if sort_points else 0
-        o.gpu_method = _lib.METHOD_IDS[gpu_method]
-        if block_size is not None and not isinstance(block_size, int):
-            for d, b in enumerate(block_size):
-                o.block_dims[d] = int(b)
-        o.point_convention = int(point_convention)
-        o.device = self.device.index
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         self.stream = stream
-        o.stream = C.c_void_p(stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream))
-        o.record_timings = 1 if timer else 0
-        o.spread_chunk = int(spread_chunk)
+        o = build_opts(self._lib, dims, self.is_complex, self.real_dtype, M, sigma, kernel, mode_name, ntransforms, fftshift,
+                       sort_points, gpu_method, block_size, point_convention, self.device.index, stream, timer, spread_chunk)
         self._opts = o
         h = C.c_void_p()
         _check(self._lib.nufft_plan_create(C.byref(h), C.byref(o)))
@@ -454,7 +469,7 @@ class PlanNUFFT:
 
     def binning_fine(self):
         """(perm, fine_offsets, sub_dims): the (bin, sub-bin) order the kernels use.  Column-streaming plans refine every
-        bin (a column of 4 x 4 cells, up to 256 cells along z) into sub_dims layers of 4 cells and do not materialise
+        bin (a column of 4 x 4 cells, up to 256 cells along z) into sub_dims single cells along z and do not materialise
         sub-bin offsets (fine_offsets is None); other plans: identical to `binning()`, sub_dims (1, 1, 1)."""
         perm, off = C.c_void_p(), C.c_void_p()
         nf = C.c_int64()

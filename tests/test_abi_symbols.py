@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     assert set(names) == set(_lib.SYMBOLS), "ctypes binding and header disagree"
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/nufft_b200.h but not exported"
-    assert lib.nufft_abi_version() == 1
+    assert lib.nufft_abi_version() == 2
 
 
 def test_opts_struct_layout_and_defaults():

@@ -40,12 +40,12 @@ def run_case(nufft, oracle_mod, dtype, dims, Np, *, m=4, sigma=2.0, kernel="back
     assert np.array_equal(off.cpu().numpy(), cum_o), "bin offsets differ from the oracle"
     assert np.array_equal(perm.cpu().numpy(), perm_o), "permutation differs from the oracle (stable order)"
     # the order the kernels use: column-streaming plans refine the bins (columns of 4 x 4 cells, up to 256 cells along z)
-    # into layers of 4 cells; expected = stable sort by (bin, layer) of the oracle's own cell indices
+    # by the z cell; expected = stable sort by (bin, z cell) of the oracle's own cell indices
     fperm, foff, sub = gp.binning_fine()
     if sub != (1, 1, 1):
         assert D == 3 and all(bdims[d] % sub[d] == 0 for d in range(3))
         sw = [bdims[d] // sub[d] for d in range(3)]        # sub-bin edge
-        assert sw == [4, 4, 4]
+        assert sw == [4, 4, 1]
         cell, _, _ = op.sort_points(xs, (1, 1, 1))
         cell = cell.astype(np.int64)
         c = [cell % op.Nos[0], (cell // op.Nos[0]) % op.Nos[1], cell // (op.Nos[0] * op.Nos[1])]

@@ -18,13 +18,15 @@ def _points_1d(rng, Np, rt):
     return x.astype(rt)
 
 
-SLACK = 1.25   # the reference tuned its bounds on ITS random draw (Julia Xoshiro(42), not reproducible here);
-               # a different draw moves the measured error by a few per cent (e.g. KB, M = 7, sigma = 2 sits at 0.99x-1.01x)
+# The reference's bounds are used AS THEY ARE (no global slack).  They were tuned on the reference's own random draw (Julia
+# Xoshiro(42), not reproducible here); with numpy's draw exactly one case sits 0.9 % above its bound (measured 3.035e-13 against
+# 3.007e-13) and is listed individually:
+SLACK_EXCEPTIONS = {("float64", "kaiser_bessel", 7, 2.0): 1.05}
 
 
 def _threshold(dtype, kernel, M, sigma):
-    """check_nufft_error, test/accuracy.jl:7-78 (times SLACK)."""
-    return SLACK * _threshold_ref(dtype, kernel, M, sigma)
+    """check_nufft_error, test/accuracy.jl:7-78."""
+    return SLACK_EXCEPTIONS.get((np.dtype(dtype).name, kernel, M, sigma), 1.0) * _threshold_ref(dtype, kernel, M, sigma)
 
 
 def _threshold_ref(dtype, kernel, M, sigma):
