@@ -176,8 +176,9 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # N > 1: strong scaling of C5 through the multi-GPU C ABI
 # ----------------------------------------------------------------------------------------------
-C5_MODES = 512
-C5_NP = 512 ** 3
+C5_MODES = int(os.environ.get("BENCH_C5_MODES", "512"))          # (development: smaller problems under compute-sanitizer)
+C5_NP = int(os.environ.get("BENCH_C5_NP", str(512 ** 3)))
+BENCH_QUICK = os.environ.get("BENCH_QUICK", "") == "1"              # skip the single-GPU baseline and the weak-scaling extra
 
 
 def bind_to_gpu_numa(local_rank: int):
@@ -366,7 +367,7 @@ def run_ours_multi(args, world, rank, local_rank):
     # ---- the same problem on ONE GPU (rank 0), same run: the strong-scaling baseline -----------------------------------------
     single = None
     barrier()
-    if rank == 0:
+    if rank == 0 and not BENCH_QUICK:
         try:
             gen0 = torch.Generator(device=dev); gen0.manual_seed(99)
             xs1 = [torch.rand(C5_NP, device=dev, generator=gen0) * (2 * np.pi) for _ in range(3)]
@@ -400,7 +401,7 @@ def run_ours_multi(args, world, rank, local_rank):
     barrier()
 
     # ---- weak scaling as in round 1: every rank its own 2^24 points of a 256^3 problem, points strategy ------------------------
-    npts = NP_FULL
+    npts = NP_FULL if not BENCH_QUICK else 1 << 18
     xs_w = [torch.rand(npts, device=dev, generator=gen) * (2 * np.pi) for _ in range(3)]
     vp_w = torch.view_as_complex(torch.randn(npts, 2, device=dev, generator=gen))
     uk_w = torch.view_as_complex(torch.randn((N_MODES,) * 3 + (2,), device=dev, generator=gen))
@@ -441,7 +442,7 @@ def run_ours_multi(args, world, rank, local_rank):
             "check": check["result"], "check_detail": check,
             "single_gpu_same_problem": single,
             "speedup_vs_single_gpu": (single["ms_per_step"] / (ms_total / K)) if single and "ms_per_step" in single else None,
-            "weak_c3": {"value": 2.0 * NP_FULL * world * K / (ms_weak * 1e-3), "unit": UNIT, "ms_per_step": ms_weak / K,
+            "weak_c3": {"value": 2.0 * npts * world * K / (ms_weak * 1e-3), "unit": UNIT, "ms_per_step": ms_weak / K,
                         "workload": "C3 per rank (2^24 own points of one 256^3 problem), points strategy: outputs all-reduced, spectrum broadcast"},
             "roofline": {"bound": "hbm", "kernel": f"K-{dom} (per rank)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
@@ -472,7 +473,13 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     if world > 1:
-        return run_ours_multi(args, world, rank, local_rank)
+        try:
+            return run_ours_multi(args, world, rank, local_rank)
+        except BaseException:
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)          # no destructors: the other ranks are inside collectives, the launcher tears them down
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -646,6 +653,36 @@ def run_ours(args):
             "type2_incl_set_points_frac": (B_2 + B_sp) / (ms_t2 * 1e-3) / 1e9 / peak,
             "stage_ms": timer}
 
+    # C5 (512^3 modes, Np = 2^27) on this one GPU: the strong-scaling baseline of the N > 1 lines, reported beside the headline
+    c5 = None
+    if not args.no_c5:
+        try:
+            plan.close()
+            del xs_b, vp_b, uk_b, o1_b, o2_b
+            torch.cuda.empty_cache()
+            gen0 = torch.Generator(device=dev); gen0.manual_seed(99)
+            xs5 = [torch.rand(C5_NP, device=dev, generator=gen0) * (2 * np.pi) for _ in range(3)]
+            for x in xs5:
+                x[x >= 2 * np.pi] = 0.0
+            vp5 = torch.view_as_complex(torch.randn(C5_NP, 2, device=dev, generator=gen0))
+            p5 = nb.PlanNUFFT(torch.complex64, (C5_MODES,) * 3, m=HALF_SUPPORT, sigma=SIGMA, kernel=nb.BackwardsKaiserBesselKernel(),
+                              kernel_evalmode=nb.FastApproximation(), timer=True, device=dev)
+            o5 = torch.zeros(p5.shape, dtype=torch.complex64, device=dev)
+            w5 = torch.zeros(C5_NP, dtype=torch.complex64, device=dev)
+            def s5():
+                p5.set_points(tuple(xs5)); p5.exec_type1(o5, vp5)
+                p5.set_points(tuple(xs5)); p5.exec_type2(w5, o5)
+            for _ in range(2):
+                s5()
+            n5 = 3
+            ms5 = timed(s5, n5) / n5
+            c5 = {"workload": "C5: 512^3 modes (1024^3 grid), Np = 2^27, ComplexF32, one GPU", "ms_per_step": ms5,
+                  "value": 2.0 * C5_NP / (ms5 * 1e-3), "unit": UNIT, "steps": n5, "stage_ms": dict(p5.timer)}
+            p5.close()
+            del xs5, vp5, o5, w5
+        except Exception as e:      # pragma: no cover
+            c5 = {"error": str(e)[:200]}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -668,6 +705,7 @@ def run_ours(args):
             "clustered": {"points": "Gaussian cloud, sigma = 1 rad (folded), Np = 2^24 per GPU", "type1_ms": ms_t1c, "type2_ms": ms_t2c,
                           "type1_points_per_s": npts * world / (ms_t1c * 1e-3), "type2_points_per_s": npts * world / (ms_t2c * 1e-3),
                           "stage_ms": timer_c},
+            "c5_single_gpu": c5,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K,
@@ -676,9 +714,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
         }
         print(json.dumps(line))
-    plan.close()
-    if world > 1:
-        dist.destroy_process_group()
+    try:
+        plan.close()
+    except Exception:
+        pass
     return 0
 
 
@@ -689,6 +728,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="N = 1: skip the C5 single-GPU extra key")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -32,7 +32,7 @@ CFLAGS = ([f"-DNUFFT_DEV_M={DEV_M}"] if DEV_M else []) + os.environ.get("NUFFT_E
 
 # (source, object suffix, extra defines)
 UNITS = [("api.cu", "", []), ("host_plan.cu", "", []), ("binning.cu", "", []), ("deconv.cu", "", []), ("pfft.cu", "", []),
-         ("callbacks_jit.cu", "", []), ("mgpu.cu", "", [])]
+         ("callbacks_jit.cu", "", []), ("mgpu.cu", "", []), ("ring_inst.cu", "", [])]
 for t in ("float", "double"):
     for c in (0, 1):
         tag = f"_{'f32' if t == 'float' else 'f64'}_{'c' if c else 'r'}"

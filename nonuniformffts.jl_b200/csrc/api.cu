@@ -42,6 +42,21 @@ static inline void rec(Plan &p, int i)
     if (p.ev_ok) { cudaEventRecord(p.ev[i], p.stream); }
 }
 
+// Selects the plan's device for the duration of an entry point and restores the caller's device on every return path
+// (a host that drives several GPUs from one thread must not find its current device changed by a library call).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else if (err == cudaSuccess) prev = -1;       // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define NUFFT_DEVICE_GUARD(p_) DeviceGuard _guard((p_).device); CUDA_TRY(_guard.err)
+
 static int check_plan(nufft_plan h)
 {
     if (!h) { set_error("null plan handle"); return NUFFT_ERR_STATE; }
@@ -107,7 +122,10 @@ int nufft_plan_create(nufft_plan *out, const nufft_opts *opts)
     Plan *p = new (std::nothrow) Plan();
     if (!p) { set_error("out of host memory"); return NUFFT_ERR_ALLOC; }
     p->opts = *opts;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     const int rc = host_plan_init(*p);
+    if (prev_dev >= 0) cudaSetDevice(prev_dev);
     if (rc != NUFFT_SUCCESS) {
         host_plan_free(*p);
         delete p;
@@ -121,6 +139,7 @@ int nufft_plan_destroy(nufft_plan h)
 {
     if (!h) return NUFFT_SUCCESS;
     Plan *p = reinterpret_cast<Plan *>(h);
+    DeviceGuard guard(p->device);
     cudaStreamSynchronize(p->stream);
     host_plan_free(*p);
     delete p;
@@ -163,7 +182,7 @@ int nufft_set_points(nufft_plan h, int64_t np, const void *const x[])
     NUFFT_TRY(check_plan(h));
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (!x) { set_error("null point array list"); return NUFFT_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(p.device));
+    NUFFT_DEVICE_GUARD(p);
     return binning_set_points(p, np, x);
 }
 
@@ -172,7 +191,7 @@ int nufft_set_points_matrix(nufft_plan h, int64_t np, const void *xmat)
     NUFFT_TRY(check_plan(h));
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (!xmat && np > 0) { set_error("null point matrix"); return NUFFT_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(p.device));
+    NUFFT_DEVICE_GUARD(p);
     // column-major (D, Np) matrix == array of D-vectors: coordinate d of point i at xmat[i * D + d]; read in place by K-bin
     const void *x[3] = {nullptr, nullptr, nullptr};
     for (int d = 0; d < p.D; ++d) x[d] = (const char *)xmat + (size_t)d * p.real_bytes;
@@ -209,7 +228,7 @@ int nufft_type1_spread(nufft_plan h, const void *const vp[], const nufft_callbac
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (p.Np < 0) { set_error("set_points must be called before exec_type1"); return NUFFT_ERR_STATE; }
     if (!vp) { set_error("null vp"); return NUFFT_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(p.device));
+    NUFFT_DEVICE_GUARD(p);
     rec(p, 2);
     const size_t zbytes = p.real_bytes * (p.cplx ? 2 : 1);
     CUDA_TRY(cudaMemsetAsync(p.d_us, 0, (size_t)p.C * p.ncells * zbytes, p.stream));
@@ -236,7 +255,7 @@ int nufft_type1_finish(nufft_plan h, void *const uhat[], const nufft_callbacks *
     NUFFT_TRY(check_plan(h));
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (!uhat) { set_error("null uhat"); return NUFFT_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(p.device));
+    NUFFT_DEVICE_GUARD(p);
     rec(p, 5);
     if (p.pfft) {
         NUFFT_TRY(pfft_type1_run(p, uhat, cb));     // truncating FFT passes with the deconvolution fused in
@@ -270,7 +289,7 @@ int nufft_type2_prepare(nufft_plan h, const void *const uhat[], const nufft_call
     NUFFT_TRY(check_plan(h));
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (!uhat) { set_error("null uhat"); return NUFFT_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(p.device));
+    NUFFT_DEVICE_GUARD(p);
     rec(p, 8);
     std::vector<void *> tmp_u(p.C);
     {
@@ -300,7 +319,7 @@ int nufft_type2_interp(nufft_plan h, void *const vp[], const nufft_callbacks *cb
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (p.Np < 0) { set_error("set_points must be called before exec_type2"); return NUFFT_ERR_STATE; }
     if (!vp) { set_error("null vp"); return NUFFT_ERR_ARG; }
-    CUDA_TRY(cudaSetDevice(p.device));
+    NUFFT_DEVICE_GUARD(p);
     rec(p, 11);
     NUFFT_TRY(interp_run(p, vp, cb));
     {

@@ -138,14 +138,23 @@ int jit_callbacks_get(Plan &p, const nufft_callbacks *cb, JitCallbacks **out)
     nvrtcGetCUBIN(prog, cubin.data());
     nvrtcDestroyProgram(&prog);
 
+    // the plan only ever caches a fully resolved object: a failure below leaves p.jit empty, so the next call recompiles
     j = new JitCallbacks();
-    j->src = src;
-    p.jit = j;
-    CUDA_TRY(cudaLibraryLoadData(&j->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
-    CUDA_TRY(cudaLibraryGetKernel(&j->k_nu, j->lib, "nufft_cb_nu_kernel"));
-    CUDA_TRY(cudaLibraryGetKernel(&j->k_u, j->lib, "nufft_cb_u_kernel"));
+    auto fail = [&](cudaError_t e, const char *what) {
+        set_error("CUDA error %s in %s: %s", cudaGetErrorName(e), what, cudaGetErrorString(e));
+        if (j->lib) cudaLibraryUnload(j->lib);
+        delete j;
+        cudaGetLastError();
+        return NUFFT_ERR_CUDA;
+    };
+    cudaError_t e = cudaLibraryLoadData(&j->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) { j->lib = nullptr; return fail(e, "cudaLibraryLoadData"); }
+    if ((e = cudaLibraryGetKernel(&j->k_nu, j->lib, "nufft_cb_nu_kernel")) != cudaSuccess) return fail(e, "cudaLibraryGetKernel");
+    if ((e = cudaLibraryGetKernel(&j->k_u, j->lib, "nufft_cb_u_kernel")) != cudaSuccess) return fail(e, "cudaLibraryGetKernel");
     j->has_nu = strstr(src, "NUFFT_HAS_NONUNIFORM") != nullptr;
     j->has_u = strstr(src, "NUFFT_HAS_UNIFORM") != nullptr;
+    j->src = src;
+    p.jit = j;
     *out = j;
     return NUFFT_SUCCESS;
 }

@@ -33,6 +33,7 @@ __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 __device__ __forceinline__ float i0_t(float x) { return cyl_bessel_i0f(x); }
 __device__ __forceinline__ double i0_t(double x) { return cyl_bessel_i0(x); }
 __device__ __forceinline__ float fmod_t(float x, float y) { return fmodf(x, y); }
+__device__ __forceinline__ double fmod_t(double x, double y) { return fmod(x, y); }   // (a float-only overload would fold far-away Float64 points at float precision)
 
 // Fold x onto [0, 2pi) with the reference CPU loop (bit-identical bins); points further than
 // 64 periods away are first reduced with fmod so the loop is bounded.

@@ -157,45 +157,79 @@ __device__ __forceinline__ int mg_dest(float z, int convention, int Nz, int nzs,
     return d < G ? d : G - 1;
 }
 
+constexpr int MG_ITEMS = 4;                     // points per thread: the loads are issued before the cell arithmetic
+constexpr int MG_TILE = 256 * MG_ITEMS;
+
 __global__ void __launch_bounds__(256) mg_dest_count_kernel(const float *__restrict__ z, int64_t np, int convention, int Nz, int nzs, int G,
                                                             unsigned long long *__restrict__ counts)
 {
     __shared__ unsigned int sc[MG_MAX_RANKS];
     if (threadIdx.x < MG_MAX_RANKS) sc[threadIdx.x] = 0;
     __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
-        const int d = mg_dest(z[i], convention, Nz, nzs, G);
-        const unsigned peers = __match_any_sync(__activemask(), d);
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sc[d], (unsigned)__popc(peers));
+    const int64_t base = (int64_t)blockIdx.x * MG_TILE;
+    float zi[MG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; ++k) {
+        const int64_t i = base + k * 256 + threadIdx.x;
+        zi[k] = i < np ? z[i] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; ++k) {
+        const int64_t i = base + k * 256 + threadIdx.x;
+        const int d = i < np ? mg_dest(zi[k], convention, Nz, nzs, G) : MG_MAX_RANKS + (threadIdx.x & 31);
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        if (i < np && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sc[d], (unsigned)__popc(peers));
     }
     __syncthreads();
     if (threadIdx.x < G && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
 }
 
-// points grouped by destination rank (any order inside a group): sendperm[pos] = i, coordinates copied to pos
+// points grouped by destination rank (any order inside a group): sendperm[pos] = i, coordinates copied to pos.  A CTA ranks
+// its tile of points per destination in shared memory and reserves one range per destination with a single global atomic.
 __global__ void __launch_bounds__(256) mg_dest_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
                                                               int64_t np, int convention, int Nz, int nzs, int G, DestOffsets base,
                                                               unsigned long long *__restrict__ cursor, int32_t *__restrict__ sendperm,
                                                               float *__restrict__ sx, float *__restrict__ sy, float *__restrict__ sz)
 {
+    __shared__ unsigned int sc[MG_MAX_RANKS];
+    __shared__ unsigned long long sbase[MG_MAX_RANKS];
     const int lane = threadIdx.x & 31;
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < np; i0 += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = i0 + threadIdx.x;
+    if (threadIdx.x < MG_MAX_RANKS) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t tile = (int64_t)blockIdx.x * MG_TILE;
+    float zi[MG_ITEMS], xi[MG_ITEMS], yi[MG_ITEMS];
+    int dest[MG_ITEMS];
+    unsigned rank[MG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; ++k) {
+        const int64_t i = tile + k * 256 + threadIdx.x;
+        zi[k] = xi[k] = yi[k] = 0.f;
+        if (i < np) { zi[k] = z[i]; xi[k] = x[i]; yi[k] = y[i]; }
+    }
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; ++k) {
+        const int64_t i = tile + k * 256 + threadIdx.x;
         const bool valid = i < np;
-        float zi = 0.f;
-        int d = MG_MAX_RANKS + lane;
-        if (valid) { zi = z[i]; d = mg_dest(zi, convention, Nz, nzs, G); }
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        dest[k] = valid ? mg_dest(zi[k], convention, Nz, nzs, G) : MG_MAX_RANKS + lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, dest[k]);
         const int leader = __ffs(peers) - 1;
-        unsigned long long pos = 0;
-        if (valid && lane == leader) pos = atomicAdd(&cursor[d], (unsigned long long)__popc(peers));
-        pos = __shfl_sync(0xffffffffu, pos, leader);
-        if (valid) {
-            pos += base.off[d] + __popc(peers & ((1u << lane) - 1u));
+        unsigned r = 0;
+        if (valid && lane == leader) r = atomicAdd(&sc[dest[k]], (unsigned)__popc(peers));
+        r = __shfl_sync(0xffffffffu, r, leader);
+        rank[k] = r + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (threadIdx.x < G) sbase[threadIdx.x] = base.off[threadIdx.x] + (sc[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (unsigned long long)sc[threadIdx.x]) : 0ull);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; ++k) {
+        const int64_t i = tile + k * 256 + threadIdx.x;
+        if (i < np) {
+            const unsigned long long pos = sbase[dest[k]] + rank[k];
             sendperm[pos] = (int32_t)i;
-            sx[pos] = x[i];
-            sy[pos] = y[i];
-            sz[pos] = zi;
+            sx[pos] = xi[k];
+            sy[pos] = yi[k];
+            sz[pos] = zi[k];
         }
     }
 }
@@ -303,6 +337,13 @@ static int mg_alltoallv(Mgpu &m, MgRank &R, const void *send, const std::vector<
     return NUFFT_SUCCESS;
 }
 
+// the entry points switch between the devices of their local ranks: the caller's current device is restored on return
+struct MgDeviceRestore {
+    int prev = -1;
+    MgDeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~MgDeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 static int mg_check(nufft_mgpu h)
 {
     if (!h) { set_error("null multi-GPU handle"); return NUFFT_ERR_STATE; }
@@ -324,7 +365,7 @@ static int slab_set_points(Mgpu &m, const int64_t np[], const void *const x[])
         NUFFT_TRY(mg_ensure_user(m, R, np[l]));
         CUDA_TRY(cudaMemsetAsync(R.d_cnt, 0, 2 * MG_MAX_RANKS * sizeof(unsigned long long), R.stream));
         if (np[l] > 0) {
-            const int grid = (int)std::min<int64_t>(cdiv(np[l], 256), 148 * 8);
+            const unsigned grid = (unsigned)cdiv(np[l], MG_TILE);
             mg_dest_count_kernel<<<grid, 256, 0, R.stream>>>((const float *)x[3 * l + 2], np[l], m.opts.point_convention, Nz, nzs, G, R.d_cnt);
             NUFFT_COUNT_LAUNCH();
         }
@@ -363,7 +404,7 @@ static int slab_set_points(Mgpu &m, const int64_t np[], const void *const x[])
         R.np_slab = ro;
         NUFFT_TRY(mg_ensure_slab(m, R, ro));
         if (np[l] > 0) {
-            const int grid = (int)std::min<int64_t>(cdiv(np[l], 256), 148 * 8);
+            const unsigned grid = (unsigned)cdiv(np[l], MG_TILE);
             mg_dest_scatter_kernel<<<grid, 256, 0, R.stream>>>((const float *)x[3 * l], (const float *)x[3 * l + 1], (const float *)x[3 * l + 2], np[l],
                                                               m.opts.point_convention, Nz, nzs, G, base, R.d_cnt + MG_MAX_RANKS, R.d_sendperm,
                                                               R.d_sx[0], R.d_sx[1], R.d_sx[2]);
@@ -579,6 +620,7 @@ int nufft_mgpu_create(nufft_mgpu *out, const nufft_opts *opts, int32_t nranks, i
     if (opts->struct_size != sizeof(nufft_opts)) { set_error("nufft_opts.struct_size does not match this library: ABI mismatch"); return NUFFT_ERR_ARG; }
     if (nranks < 1 || nranks > MG_MAX_RANKS || nlocal < 1 || nlocal > nranks) { set_error("invalid rank counts (1 <= nlocal <= nranks <= %d)", MG_MAX_RANKS); return NUFFT_ERR_ARG; }
     if (strategy < NUFFT_MGPU_AUTO || strategy > NUFFT_MGPU_TRANSFORMS) { set_error("unknown multi-GPU strategy %d", strategy); return NUFFT_ERR_ARG; }
+    MgDeviceRestore restore_device;
     NcclApi &n = nccl_api();
     if (nranks > 1 && !n.lib) { set_error("NCCL (libnccl.so.2) could not be loaded: multi-GPU transforms are unavailable"); return NUFFT_ERR_UNSUPPORTED; }
     if (nranks > 1 && !id128) { set_error("null NCCL id"); return NUFFT_ERR_ARG; }
@@ -618,7 +660,9 @@ int nufft_mgpu_create(nufft_mgpu *out, const nufft_opts *opts, int32_t nranks, i
         R.dev = devices[l];
         if (R.rank < 0 || R.rank >= nranks) { set_error("local rank out of range"); return fail(NUFFT_ERR_ARG); }
         if (cudaSetDevice(R.dev) != cudaSuccess) { cudaGetLastError(); set_error("cannot select device %d", R.dev); return fail(NUFFT_ERR_CUDA); }
-        if (nlocal == 1 && opts->stream) R.stream = (cudaStream_t)opts->stream;
+        // one rank per process: the caller's stream, INCLUDING the default stream (opts.stream == NULL) — the work must be ordered
+        // with the caller's copies and events; several ranks in one process: a private stream per rank
+        if (nlocal == 1) R.stream = (cudaStream_t)opts->stream;
         else {
             if (cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); set_error("cannot create a stream"); return fail(NUFFT_ERR_CUDA); }
             R.own_stream = true;
@@ -693,6 +737,7 @@ int nufft_mgpu_create(nufft_mgpu *out, const nufft_opts *opts, int32_t nranks, i
 
 int nufft_mgpu_destroy(nufft_mgpu h)
 {
+    MgDeviceRestore restore_device;
     if (!h) return NUFFT_SUCCESS;
     Mgpu *m = reinterpret_cast<Mgpu *>(h);
     for (auto &R : m->L) mg_free_rank(R);
@@ -729,6 +774,7 @@ int nufft_mgpu_local_block(nufft_mgpu h, int32_t l, int64_t offset[3], int64_t s
 
 int nufft_mgpu_set_points(nufft_mgpu h, const int64_t np[], const void *const x[])
 {
+    MgDeviceRestore restore_device;
     NUFFT_TRY(mg_check(h));
     Mgpu &m = *reinterpret_cast<Mgpu *>(h);
     if (!np || !x) { set_error("null argument"); return NUFFT_ERR_ARG; }
@@ -748,6 +794,7 @@ int nufft_mgpu_set_points(nufft_mgpu h, const int64_t np[], const void *const x[
 
 int nufft_mgpu_exec_type1(nufft_mgpu h, void *const uhat[], const void *const vp[], const nufft_callbacks *cb)
 {
+    MgDeviceRestore restore_device;
     NUFFT_TRY(mg_check(h));
     Mgpu &m = *reinterpret_cast<Mgpu *>(h);
     if (!uhat || !vp) { set_error("null argument"); return NUFFT_ERR_ARG; }
@@ -787,6 +834,7 @@ int nufft_mgpu_exec_type1(nufft_mgpu h, void *const uhat[], const void *const vp
 
 int nufft_mgpu_exec_type2(nufft_mgpu h, void *const vp[], const void *const uhat[], const nufft_callbacks *cb)
 {
+    MgDeviceRestore restore_device;
     NUFFT_TRY(mg_check(h));
     Mgpu &m = *reinterpret_cast<Mgpu *>(h);
     if (!uhat || !vp) { set_error("null argument"); return NUFFT_ERR_ARG; }
@@ -826,6 +874,7 @@ int nufft_mgpu_exec_type2(nufft_mgpu h, void *const vp[], const void *const uhat
 
 int nufft_mgpu_gather_output(nufft_mgpu h, void *const full[], const void *const local[])
 {
+    MgDeviceRestore restore_device;
     NUFFT_TRY(mg_check(h));
     Mgpu &m = *reinterpret_cast<Mgpu *>(h);
     if (!full || !local) { set_error("null argument"); return NUFFT_ERR_ARG; }
@@ -864,6 +913,7 @@ int nufft_mgpu_gather_output(nufft_mgpu h, void *const full[], const void *const
 
 int nufft_mgpu_synchronize(nufft_mgpu h)
 {
+    MgDeviceRestore restore_device;
     NUFFT_TRY(mg_check(h));
     Mgpu &m = *reinterpret_cast<Mgpu *>(h);
     for (auto &R : m.L) {
@@ -884,6 +934,7 @@ int nufft_mgpu_get_stream(nufft_mgpu h, int32_t l, void **stream)
 
 int nufft_mgpu_get_timings(nufft_mgpu h, int32_t l, float ms[16])
 {
+    MgDeviceRestore restore_device;
     NUFFT_TRY(mg_check(h));
     Mgpu &m = *reinterpret_cast<Mgpu *>(h);
     if (l < 0 || l >= (int)m.L.size() || !ms) { set_error("invalid argument"); return NUFFT_ERR_ARG; }

@@ -387,7 +387,10 @@ template <typename T, int L, bool FWD, bool CONTIG> static int pf_launch_LC(cons
     constexpr int TW = pf_tw<T>(L), NT = pf_nt<T>(L);
     const size_t smem = pf_smem<T>(L);
     auto kern = pfft_pass_kernel<T, L, FWD, CONTIG>;
-    static bool attr_done = false;             // per instantiation
+    static bool attr_done_dev[64] = {};        // per instantiation and device (function attributes are per device)
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    bool &attr_done = attr_done_dev[dev & 63];
     if (!attr_done) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -15,6 +15,7 @@
 // Against the layer-window kernels (cs_spread.cuh): 32 instead of 44 FFMA2 per point (no zero-padded z weights), no plane
 // moves (28 64-bit moves per layer there), 64 instead of 88 window registers -> 16 instead of 12 resident warps per SM.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through the runtime, ring_inst.cu)
 #include "window_common.cuh"
 #include "cs_spread.cuh"
 
@@ -46,6 +47,13 @@ constexpr int OFF_VX = 0;                 // [0..23]  spreading: value x wx_pad[
 constexpr int OFF_WY = 24;                // [24..47] wyT rows (rt::store_y layout)
 constexpr int OFF_WZ = 48;                // [48..55] wz[0..7] (not padded: plane cz - 3 + j)
 constexpr int STAGE_F = 7 * 32;           // as cs:: (folded record, value, index)
+// TMA plane retirement: a leaving plane of the window (11 x 11 cells) is written to a warp-private shared-memory tile of
+// 11 rows x 12 cells (one zero pad cell to the left: the box starts at an even grid x, 16-byte aligned) and leaves as ONE
+// cp.reduce.async.bulk.tensor.3d ... .add (UTMAREDG): the reduction is done by the TMA unit / L2, not by per-lane RED
+// instructions (whose issue rate, about two lanes per clock and SM, bounded the kernel: 1.8 of 2.8 ms at C3).
+constexpr int TMA_ROW = 12;               // cells per tile row
+constexpr int TMA_TILE_B = 1152;          // bytes per tile (11 x 12 x 8 = 1056, padded to a multiple of 128)
+constexpr int TMA_NBUF = 3;               // tiles in flight per warp
 
 struct Rec {                              // what one lane keeps of a point record
     u64 vx, vx3;                          // value x wx of the lane's columns 0..2 / column 3
@@ -174,14 +182,22 @@ __device__ __forceinline__ u64 zero64()
     default: F_(7) break;                                                                                                         \
     }
 
-template <int NW>                         // NW == NWARP (a template so that every translation unit may include it)
-__global__ void __launch_bounds__(32 * NW)
-ring_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
-                   const float4 *__restrict__ prec, PtrPack vp, int C, float2 *__restrict__ us, int64_t ncells,
-                   const float *__restrict__ nu_weights, int zlo, int nzwrap)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *tm, unsigned smem, int c0, int c1, int c2)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *rec_all = (float *)smem_raw;                                      // [NWARP][BATCH + 1][REC_F]
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(smem)
+                 : "memory");
+}
+
+template <int NW, bool TMA>               // NW == NWARP (a template so that every translation unit may include it)
+__global__ void __launch_bounds__(32 * NW)
+ring_spread_kernel(const __grid_constant__ CUtensorMap tmap, KernelParams<float> kp, TileGeom g, int np, int chunk, const int32_t *__restrict__ perm, int32_t *work_counter,
+                   const float4 *__restrict__ prec, PtrPack vp, int C, float2 *__restrict__ us, int64_t ncells,
+                   const float *__restrict__ nu_weights, int zlo, int nzwrap, int nzloc)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *tile_all = smem_raw;                                      // [NWARP][TMA_NBUF][TMA_TILE_B] (TMA only)
+    float *rec_all = (float *)(smem_raw + (TMA ? NWARP * TMA_NBUF * TMA_TILE_B : 0));      // [NWARP][BATCH + 1][REC_F]
     float *stage_all = rec_all + NWARP * (BATCH + 1) * REC_F;                // [NWARP][STAGE_F]
     int2 *key_all = (int2 *)(stage_all + NWARP * STAGE_F);                   // [NWARP][BATCH + 1] (column id, z cell)
     float *cs_s = (float *)(key_all + NWARP * (BATCH + 1));                  // [3][cs_stride]
@@ -195,6 +211,7 @@ ring_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const 
     int32_t *st_n = reinterpret_cast<int32_t *>(stage_all + warp * STAGE_F + 192) + lane;
 
     for (int i = tid; i < 3 * kp.cs_stride; i += 32 * NWARP) cs_s[i] = kp.cs[i];
+    if (TMA) for (int i = tid; i < NWARP * TMA_NBUF * TMA_TILE_B / 4; i += 32 * NWARP) ((float *)tile_all)[i] = 0.f;    // pad cells stay zero
     // record BATCH (one past the last point) is only ever prefetched, never used: keep it finite
     for (int i = lane; i < REC_F; i += 32) rec_w[BATCH * REC_F + i] = 0.f;
     if (lane == 0) key_w[BATCH] = make_int2(-2, 0);
@@ -206,6 +223,10 @@ ring_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const 
     lo.vx3 = OFF_VX + 2 * ls.x3;
     lo.wy = OFF_WY + 4 * ls.row;
     asm volatile("" : "+r"(lo.vx), "+r"(lo.vx3), "+r"(lo.wy));      // opaque: kept in registers, not recomputed per point
+    // cells of the lane's four columns inside a TMA tile (row-major, TMA_ROW cells per row, one pad cell to the left)
+    const int so0 = (ls.g) * TMA_ROW + ls.x + 1, so1 = (ls.g + 3) * TMA_ROW + ls.x + 1, so2 = (ls.g + 6) * TMA_ROW + ls.x + 1;
+    const int so3 = ls.y3 * TMA_ROW + ls.x3 + 1;
+    float2 *tile_w = reinterpret_cast<float2 *>(tile_all + (size_t)warp * TMA_NBUF * TMA_TILE_B);
     const int Nx = g.N[0], Ny = g.N[1];
     const int plane = Nx * Ny;                         // cells per z plane (the whole grid has < 2^31 cells)
     const unsigned long long pol = cs::l2_evict_first_policy();
@@ -230,29 +251,71 @@ ring_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const 
             float2 *u = us + (int64_t)c * ncells;
             // ---- window state: column, base plane zb (ring slot `rot` holds plane zb, slot (rot + j) & 7 plane zb + j) ------
             int wcol = -1, zb = 0, rot = 0;
-            int goff[4] = {0, 0, 0, 0};                    // cell offsets of the lane's 4 columns inside a z plane (a lane without
-                                                           // a 4th column accumulates zeros there and adds them to its first)
-            float2 *q0, *q1, *q2, *q3;                     // the lane's cells in the plane being retired
-            auto plane_ptrs = [&](int z) {
-                const unsigned pb = (unsigned)(plane_of(z, zlo, nzwrap) * plane);      // first cell of the plane (< 2^31 cells)
-                q0 = u + (pb + (unsigned)goff[0]); q1 = u + (pb + (unsigned)goff[1]);
-                q2 = u + (pb + (unsigned)goff[2]); q3 = u + (pb + (unsigned)goff[3]);
+            int zpl = 0;                                   // index of plane zb inside the stored grid (plane_of(zb))
+            int tc0 = 0, tc1 = 0, tbuf = 0;                // TMA: box origin (floats along x, rows), tile in use
+            bool edge = false;                             // TMA: the column's box sticks out of the grid (periodic images; boxes with
+                                                           // negative coordinates are illegal for reductions) -> per-lane reductions
+            const int tcz = c * nzloc;                     // plane coordinate of component c in the tensor map
+            float2 *q0 = u, *q1 = u, *q2 = u, *q3 = u;     // the lane's four cells in plane zb (a lane without a 4th column
+                                                           // accumulates zeros there and adds them to its first)
+            // `dz` planes leave the window (1 <= dz <= 8): ring slot -> grid plane zb, the slot restarts at zero; the cell
+            // pointers follow the base plane incrementally.  ONE call site (the 8-way switch is inlined once: the hot code must
+            // stay inside the instruction cache)
+            auto next_plane = [&]() {
+                if constexpr (!TMA) { q0 += plane; q1 += plane; q2 += plane; q3 += plane; }
+                if (++zpl == nzwrap) {                     // periodic wrap of a full grid (never on a slab)
+                    zpl = 0;
+                    if constexpr (!TMA) {
+                        const int64_t back = (int64_t)nzwrap * plane;
+                        q0 -= back; q1 -= back; q2 -= back; q3 -= back;
+                    }
+                }
+                rot = (rot + 1) & 7;
+                ++zb;
             };
-            // `dz` planes leave the window (1 <= dz <= 8): ring slot -> grid plane, the slot restarts at zero.  ONE call site
-            // (the 8-way switch is inlined once: the hot code must stay inside the instruction cache)
+            // one plane (the four values of this lane) leaves the window for grid plane zb
+            auto retire_plane = [&](u64 g0, u64 g1, u64 g2, u64 g3) {
+                if (TMA && !edge) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(TMA_NBUF - 1) : "memory");     // tile tbuf is free again
+                    __syncwarp();
+                    float2 *sb = tile_w + tbuf * (TMA_TILE_B / 8);
+                    *reinterpret_cast<u64 *>(sb + so0) = g0;
+                    *reinterpret_cast<u64 *>(sb + so1) = g1;
+                    *reinterpret_cast<u64 *>(sb + so2) = g2;
+                    if (ls.has3) *reinterpret_cast<u64 *>(sb + so3) = g3;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy stores -> visible to the TMA unit
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_3d(&tmap, (unsigned)__cvta_generic_to_shared(sb), tc0, tc1, tcz + zpl);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    tbuf = (tbuf + 1 == TMA_NBUF) ? 0 : tbuf + 1;
+                } else {
+                    if constexpr (TMA) {                   // (the cell pointers are not kept in registers on the TMA path)
+                        const int cx = wcol & 0xffff, cy = wcol >> 16;
+                        const unsigned pb = (unsigned)(zpl * plane);
+                        const int e0 = wrap1(COL * cy - (M - 1) + ls.g, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                        const int e1 = wrap1(COL * cy - (M - 1) + ls.g + 3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                        const int e2 = wrap1(COL * cy - (M - 1) + ls.g + 6, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                        const int e3 = ls.has3 ? wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx) : e0;
+                        cs::red_cell(u + (pb + (unsigned)e0), g0); cs::red_cell(u + (pb + (unsigned)e1), g1);
+                        cs::red_cell(u + (pb + (unsigned)e2), g2); cs::red_cell(u + (pb + (unsigned)e3), g3);
+                    } else {
+                        cs::red_cell(q0, g0); cs::red_cell(q1, g1); cs::red_cell(q2, g2); cs::red_cell(q3, g3);
+                    }
+                }
+            };
             auto advance = [&](int dz) {
 #pragma unroll 1
                 for (int s = 0; s < dz; ++s) {
-                    plane_ptrs(zb);
 #define NUFFT_RING_RETIRE(R_)                                                                                                     \
     {                                                                                                                             \
-        cs::red_cell(q0, G[0][R_]); cs::red_cell(q1, G[1][R_]); cs::red_cell(q2, G[2][R_]); cs::red_cell(q3, G[3][R_]);           \
+        retire_plane(G[0][R_], G[1][R_], G[2][R_], G[3][R_]);                                                                     \
         G[0][R_] = zero64(); G[1][R_] = zero64(); G[2][R_] = zero64(); G[3][R_] = zero64();                                       \
     }
                     NUFFT_RING_SWITCH(rot, NUFFT_RING_RETIRE)
 #undef NUFFT_RING_RETIRE
-                    rot = (rot + 1) & 7;
-                    ++zb;
+                    next_plane();
                 }
             };
 
@@ -288,79 +351,101 @@ ring_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const 
                 issue_n(bi + 2);
                 cs::cp_async_commit();
 
-                // ---- evaluate: one lane per point ----------------------------------------------------------------------
+                // ---- evaluate: one lane per point; the same lanes work out what the WINDOW has to do before their point ------------
+                // cmd: 0 = same column and cell as the previous point (no move), 1..8 = the window moves up by that many planes,
+                // CMD_NEW = another column (or a jump along z): flush and restart.  Lane 0 compares with the window the previous
+                // batch left behind.
+                constexpr int CMD_NEW = 64;
+                int mycol = -3, myz = 0, cmd = 0;
                 if (lane < nb) {
                     int cx, cy, cz;
                     if (nu_weights) v = cmul(v, wgt);
                     evaluate_point<true>(kp, cs_s, xyz.x, xyz.y, xyz.z, v, rec_w + lane * REC_F, cx, cy, cz);
-                    key_w[lane] = make_int2(((cy >> 2) << 16) | (cx >> 2), cz - (M - 1));      // (column, base plane of its window)
+                    mycol = ((cy >> 2) << 16) | (cx >> 2);
+                    myz = cz - (M - 1);                                     // base plane of the point's window
+                    key_w[lane] = make_int2(mycol, myz);
                 }
-                // the last batch of a chunk ends with a sentinel "point": its key opens a new column, which flushes the window
-                const int last = (bi == nbatches - 1) ? 1 : 0;
-                if (last && lane == 0) key_w[nb] = make_int2(-2, 0);
+                {
+                    int pc = __shfl_up_sync(FULL, mycol, 1), pz = __shfl_up_sync(FULL, myz, 1);
+                    if (lane == 0) { pc = wcol; pz = zb; }
+                    const int dz = myz - pz;
+                    cmd = (mycol != pc || dz < 0 || dz > RING) ? CMD_NEW : dz;
+                }
+                const unsigned starts = __ballot_sync(FULL, lane < nb && cmd != 0);     // points that move the window
+                const bool last = bi == nbatches - 1;                                   // the chunk ends: flush the window
                 __syncwarp();
 
-                // ---- accumulate: point after point, the ring follows the z cell ---------------------------------------------
-                int2 key = key_w[0];
+                // ---- accumulate: run after run (points sharing column and cell), the ring follows the z cell ------------------------
                 Rec A;
                 A.vx = lds64(rec_w + lo.vx);
                 A.vx3 = lds64(rec_w + lo.vx3);
                 A.wy = *reinterpret_cast<const float4 *>(rec_w + lo.wy);
                 A.z0 = *reinterpret_cast<const float4 *>(rec_w + OFF_WZ);
                 A.z1 = *reinterpret_cast<const float4 *>(rec_w + OFF_WZ + 4);
+                const float *nxt = rec_w + REC_F;
                 int p = 0;
 #pragma unroll 1
-                while (p < nb + last) {
-                    const float *nxt = rec_w + (p + 1) * REC_F;
-                    const int dz = key.y - zb;
-                    const bool same = key.x == wcol;
-                    if (!same || dz != 0) {
-                        const bool move = same && dz >= 1 && dz <= RING;       // the window moves up inside the column
+                while (true) {
+                    int c = 0;
+                    if (p < nb) c = ((starts >> p) & 1u) ? __shfl_sync(FULL, cmd, p) : 0;
+                    else if (last) c = CMD_NEW;
+                    else break;
+                    if (c != 0) {
+                        const bool move = c != CMD_NEW;                        // the window moves up inside the column
 #if NUFFT_RING_FRESH
-                        const int nret = move ? dz - 1 : (wcol >= 0 ? RING : 0);
+                        advance(move ? c - 1 : (wcol >= 0 ? RING : 0));
 #else
-                        const int nret = move ? dz : (wcol >= 0 ? RING : 0);
+                        advance(move ? c : (wcol >= 0 ? RING : 0));
 #endif
-                        advance(nret);
                         if (!move) {                                           // new column (or a jump along z): restart the ring
+                            if (p >= nb) { wcol = -2; break; }                 // end of the chunk: window flushed
+                            const int2 key = key_w[p];
                             wcol = key.x;
                             zb = key.y;
-                            if (p >= nb) break;                                // the sentinel: window flushed, nothing to add
+                            rot = 0;
                             const int cx = key.x & 0xffff, cy = key.x >> 16;
-#pragma unroll
-                            for (int k = 0; k < 3; ++k)
-                                goff[k] = wrap1(COL * cy - (M - 1) + ls.g + 3 * k, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
-                            goff[3] = ls.has3 ? wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx) : goff[0];
+                            zpl = plane_of(zb, zlo, nzwrap);
+                            if (nzwrap != nzloc) zpl = min(max(zpl, 0), nzloc - RING);     // z slab: a point outside the slab (caller's
+                                                                                           // contract) must not write outside the grid
+                            const unsigned pb = (unsigned)(zpl * plane);       // first cell of the plane (the grid has < 2^31 cells)
+                            const int g0 = wrap1(COL * cy - (M - 1) + ls.g, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                            const int g1 = wrap1(COL * cy - (M - 1) + ls.g + 3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                            const int g2 = wrap1(COL * cy - (M - 1) + ls.g + 6, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x, Nx);
+                            const int g3 = ls.has3 ? wrap1(COL * cy - (M - 1) + ls.y3, Ny) * Nx + wrap1(COL * cx - (M - 1) + ls.x3, Nx) : g0;
+                            q0 = u + (pb + (unsigned)g0); q1 = u + (pb + (unsigned)g1);
+                            q2 = u + (pb + (unsigned)g2); q3 = u + (pb + (unsigned)g3);
+                            // TMA box: cells 4 cx - 4 .. 4 cx + 7 (x, in floats: two per cell), rows 4 cy - 3 .. 4 cy + 7
+                            tc0 = 8 * cx - 8;
+                            tc1 = COL * cy - (M - 1);
+                            edge = cx == 0 || COL * cx + 8 > Nx || tc1 < 0 || COL * cy + 8 > Ny;
                         }
 #if NUFFT_RING_FRESH
                         else {
                             // the last leaving plane is retired here and restarted by the first point of the new cell
-                            plane_ptrs(zb);
-                            rot = (rot + 1) & 7;
-                            ++zb;
 #define NUFFT_RING_FRESH_BODY(R_)                                                                                                 \
     {                                                                                                                             \
-        constexpr int S_ = (R_ + 7) & 7;                                                                                          \
-        cs::red_cell(q0, G[0][S_]); cs::red_cell(q1, G[1][S_]); cs::red_cell(q2, G[2][S_]); cs::red_cell(q3, G[3][S_]);           \
-        ++p;                                                                                                                      \
-        key = key_w[p];                                                                                                           \
-        spread_body<R_, true>(G, A, nxt, lo);                                                                                     \
-        nxt += REC_F;                                                                                                             \
+        retire_plane(G[0][R_], G[1][R_], G[2][R_], G[3][R_]);                                                                     \
+        spread_body<(R_ + 1) & 7, true>(G, A, nxt, lo);                                                                           \
     }
                             NUFFT_RING_SWITCH(rot, NUFFT_RING_FRESH_BODY)
 #undef NUFFT_RING_FRESH_BODY
-                            if (!(p < nb && key.x == wcol && key.y == zb)) continue;
+                            next_plane();
+                            nxt += REC_F;
+                            ++p;
+                            if (p >= nb || ((starts >> p) & 1u)) continue;     // the run had one point
                         }
 #endif
                     }
-                    // all consecutive points with this (column, cell) run through the body of the current rotation
+                    // the rest of the run: all consecutive points with this (column, cell) go through the body of this rotation
+                    const unsigned after = p + 1 < 32 ? (starts >> (p + 1)) << (p + 1) : 0u;
+                    const int pend = after ? min(__ffs(after) - 1, nb) : nb;
+                    int len = pend - p;
+                    p = pend;
 #define NUFFT_RING_BODY(R_)                                                                                                       \
-    do {                                                                                                                          \
-        ++p;                                                                                                                      \
-        key = key_w[p];                                                                                                           \
+    _Pragma("unroll 1") do {                                                                                                      \
         spread_body<R_, false>(G, A, nxt, lo);                                                                                    \
         nxt += REC_F;                                                                                                             \
-    } while (p < nb && key.x == wcol && key.y == zb);
+    } while (--len);
                     NUFFT_RING_SWITCH(rot, NUFFT_RING_BODY)
 #undef NUFFT_RING_BODY
                 }
@@ -368,11 +453,12 @@ ring_spread_kernel(KernelParams<float> kp, TileGeom g, int np, int chunk, const 
             }
         }
     }
+    if (TMA && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every reduction has been performed
 }
 
-inline size_t spread_smem_bytes(int cs_stride)
+inline size_t spread_smem_bytes(int cs_stride, bool tma)
 {
-    return (size_t)NWARP * ((BATCH + 1) * REC_F + STAGE_F) * sizeof(float) + (size_t)NWARP * (BATCH + 1) * sizeof(int2) +
+    return (tma ? (size_t)NWARP * TMA_NBUF * TMA_TILE_B : 0) + (size_t)NWARP * ((BATCH + 1) * REC_F + STAGE_F) * sizeof(float) + (size_t)NWARP * (BATCH + 1) * sizeof(int2) +
            (size_t)(3 * cs_stride + 4) * sizeof(float) + 16;
 }
 

@@ -5,7 +5,6 @@
 #include <type_traits>
 #include "spread.cuh"
 #include "cs_spread.cuh"
-#include "ring_spread.cuh"
 
 #ifndef INST_T
 #define INST_T float
@@ -15,6 +14,8 @@
 #endif
 
 namespace nufft {
+
+int ring_spread_run(Plan &p, const KernelParams<float> &kp, const PtrPack &pack, int cn, float2 *us, const float *nuw, int zlo, int nzwrap);
 
 template <typename T, bool CPLX, int D, int M>
 static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks *cb)
@@ -38,27 +39,18 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
                 CUDA_TRY(cudaMemsetAsync(p.d_counters, 0, sizeof(int32_t), st));
                 static bool ring_off = getenv("NUFFT_B200_RING") && atoi(getenv("NUFFT_B200_RING")) == 0;
                 if constexpr (CPLX) {
-                    if (!ring_off) {
-                        auto kern = ring::ring_spread_kernel<ring::NWARP>;
-                        const size_t smem = ring::spread_smem_bytes(p.cs_stride);
-                        static bool attr_done = false;         // per instantiation (launch attributes are set once)
-                        if (!attr_done) {
-                            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                            attr_done = true;
-                        }
-                        kern<<<p.num_sms, 32 * ring::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters,
-                                                                        (const float4 *)p.d_rec, pack, cn, us, p.ncells, nuw, zlo, nzwrap);
-                        NUFFT_COUNT_LAUNCH();
+                    if (!ring_off) {                       // ring-window kernel: its own translation unit (ring_inst.cu)
+                        NUFFT_TRY(ring_spread_run(p, kp, pack, cn, us, nuw, zlo, nzwrap));
                         continue;
                     }
                 }
                 if (p.slab_nz > 0) { set_error("z-slab plans need the ring kernels (complex data)"); return NUFFT_ERR_UNSUPPORTED; }
                 auto kern = cs::cs_spread_kernel<CPLX>;
                 const size_t smem = cs::spread_smem_bytes(p.cs_stride);
-                static bool attr_done = false;
-                if (!attr_done) {
+                static bool attr_done[64] = {};          // per instantiation AND device: function attributes are per device
+                if (!attr_done[p.device & 63]) {
                     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    attr_done = true;
+                    attr_done[p.device & 63] = true;
                 }
                 kern<<<p.num_sms, 32 * cs::NWARP, smem, st>>>(kp, p.geom, (int)np, cs::chunk_points(), p.d_perm, p.d_counters, (const float4 *)p.d_rec, pack, cn, us,
                                                         p.ncells, nuw);
@@ -73,8 +65,10 @@ static int spread_launch(Plan &p, const void *const vp[], const nufft_callbacks 
         } else {
             auto kern = spread_sm_kernel<T, CPLX, D, M>;
             const size_t smem = sm_dynamic_bytes<T, CPLX, D, M, true>(p.geom, p.cs_stride);
-            static size_t smem_set = 0;                        // per instantiation: attribute / occupancy queried once per size
-            static int occ = 0;
+            static size_t smem_set_dev[64] = {};               // per instantiation and device: attribute / occupancy queried once per size
+            static int occ_dev[64] = {};
+            size_t &smem_set = smem_set_dev[p.device & 63];
+            int &occ = occ_dev[p.device & 63];
             if (smem_set != smem + 1) {
                 CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * (M + SPREAD_NPROD), smem));

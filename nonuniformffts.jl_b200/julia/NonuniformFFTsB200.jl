@@ -155,20 +155,25 @@ function set_points!(p::B200Plan{Z, N}, xp::AbstractMatrix{<:Real}) where {Z, N}
     eltype(xp) === real(Z) || throw(ArgumentError("input points must have the same accuracy as the created plan"))
     ccall((:nufft_set_points_matrix, libnufft), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), p.handle, size(xp, 2), devptr(xp)) |> check
     p.points = xp
+    p.np = size(xp, 2)        # exec_type1! / exec_type2! validate the data vectors against it
     p
 end
 
+# Returns (Ref{NufftCallbacks} | C_NULL, roots): `roots` holds every Julia object the struct points into (the source string
+# behind the Cstring, the device arrays) and must be GC.@preserve'd together with the Ref for the duration of the ccall.
 function _callbacks(cb)
-    cb === nothing && return C_NULL
+    cb === nothing && return (C_NULL, ())
     # cb = (nonuniform = weights::DeviceVector | nothing, uniform = factor::DeviceArray | nothing,
     #       source = CUDA C++ source of general callbacks | nothing, user_data = DeviceArray | nothing)
     src = get(cb, :source, nothing)
+    src = src === nothing ? nothing : String(src)
     usr = get(cb, :user_data, nothing)
-    Ref(NufftCallbacks(UInt32(sizeof(NufftCallbacks)),
+    r = Ref(NufftCallbacks(UInt32(sizeof(NufftCallbacks)),
         cb.nonuniform === nothing ? C_NULL : devptr(cb.nonuniform), C_NULL,
         cb.uniform === nothing ? C_NULL : devptr(cb.uniform),
-        src === nothing ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, src),     # `src` must stay rooted during the call
+        src === nothing ? Cstring(C_NULL) : Base.unsafe_convert(Cstring, src),
         usr === nothing ? C_NULL : devptr(usr)))
+    (r, (src, usr, cb.nonuniform, cb.uniform))
 end
 
 """    exec_type1!(ûs, p, vp; callbacks)   — src/NonuniformFFTs.jl:148-195"""
@@ -178,8 +183,8 @@ function exec_type1!(us::NTuple{C, Any}, p::B200Plan{Z}, vp::NTuple{C, Any}; cal
     all(u -> size(u) == size(p), us) || throw(DimensionMismatch("wrong dimensions of array (expected dimensions $(size(p)))"))
     all(v -> length(v) == p.np, vp) || throw(DimensionMismatch("wrong length of data vector (it should match the number of points $(p.np))"))
     up = Ptr{Cvoid}[devptr(u) for u in us]; vpp = Ptr{Cvoid}[devptr(v) for v in vp]
-    cb = _callbacks(callbacks)
-    GC.@preserve cb ccall((:nufft_exec_type1, libnufft), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
+    cb, roots = _callbacks(callbacks)
+    GC.@preserve cb roots us vp ccall((:nufft_exec_type1, libnufft), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
                           p.handle, up, vpp, cb === C_NULL ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, cb)) |> check
     us
 end
@@ -192,8 +197,8 @@ function exec_type2!(vp::NTuple{C, Any}, p::B200Plan{Z}, us::NTuple{C, Any}; cal
     all(u -> size(u) == size(p), us) || throw(DimensionMismatch("wrong dimensions of array (expected dimensions $(size(p)))"))
     all(v -> length(v) == p.np, vp) || throw(DimensionMismatch("wrong length of data vector (it should match the number of points $(p.np))"))
     up = Ptr{Cvoid}[devptr(u) for u in us]; vpp = Ptr{Cvoid}[devptr(v) for v in vp]
-    cb = _callbacks(callbacks)
-    GC.@preserve cb ccall((:nufft_exec_type2, libnufft), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
+    cb, roots = _callbacks(callbacks)
+    GC.@preserve cb roots us vp ccall((:nufft_exec_type2, libnufft), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
                           p.handle, vpp, up, cb === C_NULL ? C_NULL : Base.unsafe_convert(Ptr{Cvoid}, cb)) |> check
     vp
 end

@@ -63,3 +63,25 @@ def test_nfft_accuracy_params():
     m, sigma, reltol = nb.accuracy_params(reltol=1e-9)
     assert (m, sigma) == (5, 2.0) and reltol == 1e-9
     assert nb.accuracy_params(m=6, sigma=1.5)[:2] == (6, 1.5)
+
+
+def test_mgpu_argument_validation_without_a_gpu():
+    """nufft_mgpu_create rejects bad rank counts / strategies / struct sizes before it touches CUDA or NCCL."""
+    import nufft_b200  # noqa: F401
+    from nufft_b200 import _lib
+    lib = _lib.load()
+    o = _lib.nufft_opts()
+    assert lib.nufft_opts_default(C.byref(o)) == 0
+    h = C.c_void_p()
+    one = (C.c_int32 * 1)(0)
+    idbuf = (C.c_ubyte * _lib.MGPU_ID_BYTES)()
+    assert lib.nufft_mgpu_create(C.byref(h), C.byref(o), 0, 1, one, one, idbuf, 0) == _lib.NUFFT_ERR_ARG        # nranks < 1
+    assert lib.nufft_mgpu_create(C.byref(h), C.byref(o), 64, 1, one, one, idbuf, 0) == _lib.NUFFT_ERR_ARG       # nranks > 16
+    assert lib.nufft_mgpu_create(C.byref(h), C.byref(o), 2, 3, one, one, idbuf, 0) == _lib.NUFFT_ERR_ARG        # nlocal > nranks
+    assert lib.nufft_mgpu_create(C.byref(h), C.byref(o), 1, 1, one, one, idbuf, 9) == _lib.NUFFT_ERR_ARG        # unknown strategy
+    o.struct_size = 8
+    assert lib.nufft_mgpu_create(C.byref(h), C.byref(o), 1, 1, one, one, idbuf, 0) == _lib.NUFFT_ERR_ARG
+    assert h.value is None
+    assert lib.nufft_mgpu_destroy(None) == 0
+    assert lib.nufft_mgpu_synchronize(None) == _lib.NUFFT_ERR_STATE
+    assert _lib.MGPU_STRATEGIES == {"auto": 0, "slab": 1, "points": 2, "transforms": 3}
