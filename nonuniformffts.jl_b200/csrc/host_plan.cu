@@ -298,7 +298,9 @@ static bool choose_geometry(Plan &p, bool allow_cs = true)
             g.rt = 3;
             // (a z slab bins its owned planes only)
             const int64_t nzown = p.slab_nz > 0 ? p.slab_nz : p.Nos[2];
-            int Bc[3] = {4, 4, (int)std::max<int64_t>(4, std::min<int64_t>(256, p.slab_nz > 0 ? nzown : bcap(2)) / 4 * 4)};
+            int64_t seg = 256;                 // planes per z segment (tuning knob: NUFFT_B200_SEG)
+            if (const char *e = getenv("NUFFT_B200_SEG")) { const int v = atoi(e); if (v >= 8 && v <= 4096) seg = v; }
+            int Bc[3] = {4, 4, (int)std::max<int64_t>(4, std::min<int64_t>(seg, p.slab_nz > 0 ? nzown : bcap(2)) / 4 * 4)};
             tile_bytes(Bc, T, S);               // strides of the generic shared-memory kernels (unused on this path)
             int64_t nbins = 1;
             for (int d = 0; d < 3; ++d) {

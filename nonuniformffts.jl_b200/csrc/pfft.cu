@@ -25,6 +25,12 @@
 namespace nufft {
 
 constexpr int PF_MIN_L = 16, PF_MAX_L = 4096;
+#ifndef PF_TILE_BYTES
+#define PF_TILE_BYTES 32768          // line data per CTA (tuning knob)
+#endif
+#ifndef PF_MIN_CTAS
+#define PF_MIN_CTAS 4                // resident CTAs per SM the register allocation aims at (tuning knob)
+#endif
 
 template <typename T> struct PfftArgs {
     using C2 = typename Vec2<T>::type;
@@ -51,7 +57,7 @@ template <typename T> struct PfftArgs {
 template <typename T> __host__ __device__ constexpr int pf_group() { return 128 / (2 * (int)sizeof(T)); }
 template <typename T> __host__ __device__ constexpr int pf_tw(int L)
 {
-    const int maxel = 32768 / (2 * (int)sizeof(T));       // <= 32 KiB of line data per CTA: 4 CTAs per SM overlap their phases
+    const int maxel = PF_TILE_BYTES / (2 * (int)sizeof(T));       // <= 32 KiB of line data per CTA: 4 CTAs per SM overlap their phases
     return pf_group<T>() < maxel / L ? pf_group<T>() : (maxel / L > 0 ? maxel / L : 1);
 }
 template <typename T> __host__ __device__ constexpr int pf_nt(int L)
@@ -250,7 +256,7 @@ __device__ __noinline__ T pf_callback_factor(const T *fdense, const T *f0, const
 // (the tile is TW consecutive lines = one contiguous block of memory); otherwise TW consecutive elements of the
 // contiguous dimension times a strided line.
 template <typename T, int L, bool FWD, bool CONTIG>
-__global__ void __launch_bounds__(pf_nt<T>(L), 4) pfft_pass_kernel(PfftArgs<T> a)
+__global__ void __launch_bounds__(pf_nt<T>(L), PF_MIN_CTAS) pfft_pass_kernel(PfftArgs<T> a)
 {
     using C2 = typename Vec2<T>::type;
     constexpr int TW = pf_tw<T>(L), NT = pf_nt<T>(L);

