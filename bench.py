@@ -297,6 +297,7 @@ def run_ours_multi(args, world, rank, local_rank):
     launches = nb.launch_count(reset=True)
     clocks = sampler.stop() if rank == 0 else None
     stages = plan.timings(0)
+    exchange = plan.exchange
 
     def t1_only():
         plan.set_points(tuple(xs_d)); plan.exec_type1(out1_d, vp_d)
@@ -435,7 +436,8 @@ def run_ours_multi(args, world, rank, local_rank):
                                    "set_points+type1, set_points+type2 (2*Np points per step); N=1 line of this bench is C3 (the headline)",
                        "l2": "inputs larger than L2 (>= 1 GiB of grid per rank)",
                        "multi_gpu": "z-slab strategy of the C ABI (nufft_mgpu_*): point/value all-to-all, slab spreading + halo exchange, "
-                                    "slab pruned FFT with one all-to-all transpose; uniform data distributed in y"},
+                                    "slab pruned FFT with one all-to-all transpose; uniform data distributed in y",
+                       "exchange": exchange},
             "type1_points_per_s": C5_NP / (ms_t1 * 1e-3), "type2_points_per_s": C5_NP / (ms_t2 * 1e-3),
             "type1_ms": ms_t1, "type2_ms": ms_t2,
             "stage_ms_rank0": stages,

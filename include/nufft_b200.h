@@ -230,6 +230,10 @@ int  nufft_mgpu_get_stream(nufft_mgpu h, int32_t l, void **stream);
  * [7] FFT pass z  [8] type-2 FFT pass z  [9] transpose  [10] FFT passes y, x  [11] halo exchange  [12] interpolation
  * [13] value return */
 int  nufft_mgpu_get_timings(nufft_mgpu h, int32_t l, float ms[16]);
+/* how the z-slab exchanges travel: 1 = peer windows (the sender copies straight into the receiver's buffer over NVLink:
+ * CUDA IPC mappings between processes, peer access inside one; stream-ordered barriers around each exchange),
+ * 0 = NCCL send / recv (the fallback when a mapping fails on any rank, or NUFFT_B200_MGPU_P2P=0) */
+int  nufft_mgpu_exchange_mode(nufft_mgpu h, int32_t *mode);
 
 #ifdef __cplusplus
 }

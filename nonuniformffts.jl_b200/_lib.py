@@ -97,6 +97,7 @@ SYMBOLS = {
     "nufft_mgpu_synchronize": (C.c_int, [_VP]),
     "nufft_mgpu_get_stream": (C.c_int, [_VP, C.c_int32, C.POINTER(_VP)]),
     "nufft_mgpu_get_timings": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_float)]),
+    "nufft_mgpu_exchange_mode": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
 }
 MGPU_STRATEGIES = {"auto": 0, "slab": 1, "points": 2, "transforms": 3}
 MGPU_ID_BYTES = 128

@@ -31,7 +31,10 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstring>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -113,6 +116,16 @@ struct DestOffsets {
     unsigned long long off[MG_MAX_RANKS];
 };
 
+// peer windows: the receive buffers of the z-slab exchanges, written directly by the sending rank (cudaMemcpyAsync over NVLink
+// into memory mapped with CUDA IPC, or plain peer access inside one process) instead of NCCL send / recv pairs
+enum { W_RX0 = 0, W_RX1, W_RX2, W_RV, W_SV, W_HALO, W_GRID, W_A, W_N };
+constexpr unsigned W_DYNAMIC = 0x1fu, W_STATIC = 0xe0u;      // sized by the points (reallocated as they grow) / by the plan
+struct WinMsg {                                            // what a rank publishes about its windows
+    cudaIpcMemHandle_t h[W_N];
+    unsigned long long ptr[W_N];
+    int32_t ok, pad;
+};
+
 struct MgRank {
     int rank = 0, dev = 0;
     cudaStream_t stream = nullptr;
@@ -130,6 +143,11 @@ struct MgRank {
     std::vector<int64_t> sendcnt, sendoff, recvcnt, recvoff;
     void *d_halo = nullptr;                            // 2M - 1 planes received from the neighbours
     void *d_gather = nullptr;                          // nufft_mgpu_gather_output scratch
+    void *win[W_N][MG_MAX_RANKS] = {};                 // rank r's window buffer as this rank's device addresses it
+    bool win_ipc[W_N][MG_MAX_RANKS] = {};              // mapped with cudaIpcOpenMemHandle (closed before the owner frees it)
+    WinMsg *d_msg = nullptr, *h_msg = nullptr;         // [1 + G]: own message, all-gathered messages
+    int32_t *d_bar = nullptr, *h_flag = nullptr;       // barrier scratch / agreement flag
+    std::vector<int64_t> put_fwd, put_bwd;             // where my block starts inside rank r's receive buffer (elements)
     std::vector<int> comps;                            // TRANSFORMS: components of this rank
     cudaEvent_t ev[24] = {};
     bool ev_ok = false;
@@ -146,6 +164,9 @@ struct Mgpu {
     int kyl = 0;                                       // kept y modes per rank (SLAB)
     size_t zbytes = 8;                                 // bytes of a non-uniform value
     size_t cbytes = 8;                                 // bytes of a complex coefficient
+    bool p2p = false;                                  // SLAB exchanges through peer windows (else NCCL send / recv)
+    unsigned busy = 0;                                 // windows that local work has touched since the last barrier (same on every rank)
+    std::vector<int64_t> cap_slab_all, cap_user_all;   // every rank's buffer capacities (same rule everywhere: who reallocates is known to all)
 };
 
 // ---- kernels -----------------------------------------------------------------------------------------------------------------
@@ -184,15 +205,20 @@ __global__ void __launch_bounds__(256) mg_dest_count_kernel(const float *__restr
     if (threadIdx.x < G && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
 }
 
-// points grouped by destination rank (any order inside a group): sendperm[pos] = i, coordinates copied to pos.  A CTA ranks
-// its tile of points per destination in shared memory and reserves one range per destination with a single global atomic.
+// points grouped by destination rank (any order inside a group): sendperm[pos] = i, coordinates to pos.  A CTA ranks its tile of
+// points per destination, reserves one range per destination with a single global atomic, sorts the tile by destination in shared
+// memory and writes runs of consecutive positions.  (Writing the runs straight into the destination ranks' windows, and the same
+// fusion for the value exchanges, was measured SLOWER than copy-engine copies: 4- and 8-byte remote accesses reach ~120 GB/s
+// against ~330 GB/s — profiles/r2_mgpu_fused_put_get_experiment.txt.)
 __global__ void __launch_bounds__(256) mg_dest_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, const float *__restrict__ z,
                                                               int64_t np, int convention, int Nz, int nzs, int G, DestOffsets base,
                                                               unsigned long long *__restrict__ cursor, int32_t *__restrict__ sendperm,
                                                               float *__restrict__ sx, float *__restrict__ sy, float *__restrict__ sz)
 {
-    __shared__ unsigned int sc[MG_MAX_RANKS];
+    __shared__ unsigned int sc[MG_MAX_RANKS], stoff[MG_MAX_RANKS + 1];
     __shared__ unsigned long long sbase[MG_MAX_RANKS];
+    __shared__ float bx[MG_TILE], by[MG_TILE], bz[MG_TILE];
+    __shared__ int32_t bp[MG_TILE];
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < MG_MAX_RANKS) sc[threadIdx.x] = 0;
     __syncthreads();
@@ -220,18 +246,51 @@ __global__ void __launch_bounds__(256) mg_dest_scatter_kernel(const float *__res
     }
     __syncthreads();
     if (threadIdx.x < G) sbase[threadIdx.x] = base.off[threadIdx.x] + (sc[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (unsigned long long)sc[threadIdx.x]) : 0ull);
+    if (threadIdx.x == 32) {
+        unsigned acc = 0;
+        for (int r = 0; r < G; ++r) { stoff[r] = acc; acc += sc[r]; }
+        stoff[G] = acc;
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < MG_ITEMS; ++k) {
         const int64_t i = tile + k * 256 + threadIdx.x;
         if (i < np) {
-            const unsigned long long pos = sbase[dest[k]] + rank[k];
-            sendperm[pos] = (int32_t)i;
-            sx[pos] = xi[k];
-            sy[pos] = yi[k];
-            sz[pos] = zi[k];
+            const unsigned slot = stoff[dest[k]] + rank[k];
+            bx[slot] = xi[k]; by[slot] = yi[k]; bz[slot] = zi[k];
+            bp[slot] = (int32_t)i;
         }
     }
+    __syncthreads();
+    const unsigned ntile = stoff[G];
+    for (unsigned j = threadIdx.x; j < ntile; j += 256) {
+        int r = 0;
+        for (int t = 1; t < G; ++t) r += (j >= stoff[t]);
+        const unsigned long long pos = sbase[r] + (j - stoff[r]);
+        sendperm[pos] = bp[j];
+        sx[pos] = bx[j]; sy[pos] = by[j]; sz[pos] = bz[j];
+    }
+}
+
+// up to MG_MAX_RANKS block copies in one launch (blockIdx.y = job): the transposes and the halo planes, written into the peers' windows
+struct CopyJobs {
+    const uint4 *src[MG_MAX_RANKS];
+    uint4 *dst[MG_MAX_RANKS];
+    unsigned long long n16[MG_MAX_RANKS];
+};
+__global__ void __launch_bounds__(256) mg_multi_copy_kernel(CopyJobs j)
+{
+    const int job = blockIdx.y;
+    const unsigned long long n = j.n16[job];
+    const uint4 *__restrict__ s = j.src[job];
+    uint4 *__restrict__ d = j.dst[job];
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const uint4 a = s[i], b = s[i + stride], c = s[i + 2 * stride], e = s[i + 3 * stride];
+        d[i] = a; d[i + stride] = b; d[i + 2 * stride] = c; d[i + 3 * stride] = e;
+    }
+    for (; i < n; i += stride) d[i] = s[i];
 }
 
 template <typename V> __global__ void __launch_bounds__(256) mg_gather_kernel(V *__restrict__ dst, const V *__restrict__ src, const int32_t *__restrict__ perm, int64_t n)
@@ -278,8 +337,10 @@ static void mg_free_rank(MgRank &R)
     auto f = [](auto *&p) { if (p) { cudaFree((void *)p); p = nullptr; } };
     f(R.d_sendperm);
     for (int d = 0; d < 3; ++d) { f(R.d_sx[d]); f(R.d_rx[d]); }
-    f(R.d_sv); f(R.d_rv); f(R.d_cnt); f(R.d_halo); f(R.d_gather);
+    f(R.d_sv); f(R.d_rv); f(R.d_cnt); f(R.d_halo); f(R.d_gather); f(R.d_msg); f(R.d_bar);
     if (R.h_cnt) { cudaFreeHost(R.h_cnt); R.h_cnt = nullptr; }
+    if (R.h_msg) { cudaFreeHost(R.h_msg); R.h_msg = nullptr; }
+    if (R.h_flag) { cudaFreeHost(R.h_flag); R.h_flag = nullptr; }
     if (R.ev_ok) { for (auto &e : R.ev) cudaEventDestroy(e); R.ev_ok = false; }
     if (R.comm && nccl_api().CommDestroy) { nccl_api().CommDestroy(R.comm); R.comm = nullptr; }
     if (R.own_stream && R.stream) { cudaStreamDestroy(R.stream); R.stream = nullptr; }
@@ -290,6 +351,8 @@ static inline void mg_rec(MgRank &R, int i)
     if (R.ev_ok) cudaEventRecord(R.ev[i], R.stream);
 }
 
+static inline int64_t mg_grown(int64_t need) { return need + need / 8 + 1024; }
+
 static int mg_ensure_user(Mgpu &m, MgRank &R, int64_t np)
 {
     if (np <= R.cap_user) return NUFFT_SUCCESS;
@@ -297,7 +360,7 @@ static int mg_ensure_user(Mgpu &m, MgRank &R, int64_t np)
     f(R.d_sendperm); f(R.d_sv);
     for (int d = 0; d < 3; ++d) f(R.d_sx[d]);
     R.cap_user = 0;
-    const int64_t cap = np + np / 8 + 1024;
+    const int64_t cap = mg_grown(np);
     CUDA_TRY(cudaMalloc(&R.d_sendperm, (size_t)cap * sizeof(int32_t)));
     for (int d = 0; d < 3; ++d) CUDA_TRY(cudaMalloc(&R.d_sx[d], (size_t)cap * sizeof(float)));
     CUDA_TRY(cudaMalloc(&R.d_sv, (size_t)cap * m.zbytes));
@@ -312,14 +375,219 @@ static int mg_ensure_slab(Mgpu &m, MgRank &R, int64_t np)
     f(R.d_rv);
     for (int d = 0; d < 3; ++d) f(R.d_rx[d]);
     R.cap_slab = 0;
-    const int64_t cap = np + np / 8 + 1024;
+    const int64_t cap = mg_grown(np);
     for (int d = 0; d < 3; ++d) CUDA_TRY(cudaMalloc(&R.d_rx[d], (size_t)cap * sizeof(float)));
     CUDA_TRY(cudaMalloc(&R.d_rv, (size_t)cap * m.zbytes));
     R.cap_slab = cap;
     return NUFFT_SUCCESS;
 }
 
-// all-to-all with per-peer element counts (bytes = count * esize), self part copied on the stream
+// ---- peer windows ----------------------------------------------------------------------------------------------------------
+static void *mg_win_local(MgRank &R, int w)
+{
+    switch (w) {
+        case W_RX0: case W_RX1: case W_RX2: return R.d_rx[w - W_RX0];
+        case W_RV: return R.d_rv;
+        case W_SV: return R.d_sv;
+        case W_HALO: return R.d_halo;
+        case W_GRID: return R.plan ? R.plan->d_us : nullptr;
+        case W_A: return R.plan ? R.plan->d_pf_a : nullptr;
+    }
+    return nullptr;
+}
+
+// stream-ordered barrier over all ranks: a rank's later work starts after every rank's earlier work has finished
+static int mg_barrier(Mgpu &m)
+{
+    NcclApi &n = nccl_api();
+    NCCL_TRY(n.GroupStart());
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        NCCL_TRY(n.AllReduce(R.d_bar, R.d_bar, 1, ncclInt32, ncclSum, R.comm, R.stream));
+    }
+    NCCL_TRY(n.GroupEnd());
+    return NUFFT_SUCCESS;
+}
+
+// Around an exchange through peer windows.  BEFORE the copies a barrier is needed only if some rank may still be working on a
+// window the copies write (local work since the last barrier: the calls are collective, so `busy` is the same everywhere);
+// AFTER them always: the data has arrived once every rank's copies have completed.
+static int mg_exchange_begin(Mgpu &m, unsigned windows)
+{
+    if (m.busy & windows) { NUFFT_TRY(mg_barrier(m)); m.busy = 0; }
+    return NUFFT_SUCCESS;
+}
+static int mg_exchange_end(Mgpu &m)
+{
+    NUFFT_TRY(mg_barrier(m));
+    m.busy = 0;
+    return NUFFT_SUCCESS;
+}
+
+// the same, and the host waits for it (bounded: a peer that died must not hang this process in a destructor)
+static int mg_host_barrier(Mgpu &m, double timeout_s)
+{
+    NUFFT_TRY(mg_barrier(m));
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        if (timeout_s <= 0) { CUDA_TRY(cudaStreamSynchronize(R.stream)); continue; }
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(R.stream);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) { cudaGetLastError(); set_error("stream error while waiting for the other ranks"); return NUFFT_ERR_CUDA; }
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) {
+                set_error("timed out waiting for the other ranks");
+                return NUFFT_ERR_STATE;
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+    }
+    return NUFFT_SUCCESS;
+}
+
+static void mg_win_close(Mgpu &m, unsigned mask)
+{
+    for (auto &R : m.L) {
+        cudaSetDevice(R.dev);
+        for (int w = 0; w < W_N; ++w) {
+            if (!((mask >> w) & 1u)) continue;
+            for (int r = 0; r < MG_MAX_RANKS; ++r) {
+                if (R.win_ipc[w][r] && R.win[w][r]) cudaIpcCloseMemHandle(R.win[w][r]);
+                R.win[w][r] = nullptr;
+                R.win_ipc[w][r] = false;
+            }
+        }
+    }
+    cudaGetLastError();
+}
+
+// collective: every rank publishes the buffers of the windows in `mask` and maps its peers' ones; *all_ok = every rank succeeded
+// (veto: this rank takes part in the agreement but declines)
+static int mg_win_open(Mgpu &m, unsigned mask, bool *all_ok, bool veto = false)
+{
+    NcclApi &n = nccl_api();
+    const int G = m.nranks;
+    const bool other_processes = (int)m.L.size() < G;
+    *all_ok = false;
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        WinMsg &s = R.h_msg[0];
+        memset(&s, 0, sizeof(s));
+        s.ok = veto ? 0 : 1;
+        for (int w = 0; w < W_N && !veto; ++w) {
+            if (!((mask >> w) & 1u)) continue;
+            void *q = mg_win_local(R, w);
+            s.ptr[w] = (unsigned long long)q;
+            if (!q) { s.ok = 0; continue; }
+            if (other_processes && cudaIpcGetMemHandle(&s.h[w], q) != cudaSuccess) { cudaGetLastError(); s.ok = 0; }
+        }
+        CUDA_TRY(cudaMemcpyAsync(R.d_msg, R.h_msg, sizeof(WinMsg), cudaMemcpyHostToDevice, R.stream));
+    }
+    NCCL_TRY(n.GroupStart());
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        NCCL_TRY(n.AllGather(R.d_msg, R.d_msg + 1, sizeof(WinMsg), ncclUint8, R.comm, R.stream));
+    }
+    NCCL_TRY(n.GroupEnd());
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        CUDA_TRY(cudaMemcpyAsync(R.h_msg + 1, R.d_msg + 1, (size_t)G * sizeof(WinMsg), cudaMemcpyDeviceToHost, R.stream));
+    }
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        CUDA_TRY(cudaStreamSynchronize(R.stream));
+    }
+    bool ok = true;
+    for (int r = 0; r < G; ++r) if (!m.L[0].h_msg[1 + r].ok) ok = false;      // the same verdict on every rank
+    if (ok) {
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            for (int w = 0; w < W_N; ++w) {
+                if (!((mask >> w) & 1u)) continue;
+                for (int r = 0; r < G; ++r) {
+                    MgRank *local = nullptr;
+                    for (auto &Q : m.L) if (Q.rank == r) local = &Q;
+                    if (local) { R.win[w][r] = mg_win_local(*local, w); R.win_ipc[w][r] = false; continue; }
+                    void *q = nullptr;
+                    if (cudaIpcOpenMemHandle(&q, R.h_msg[1 + r].h[w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; continue; }
+                    R.win[w][r] = q;
+                    R.win_ipc[w][r] = true;
+                }
+            }
+        }
+    }
+    // mapping can fail on one rank only: agree
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        *R.h_flag = ok ? 1 : 0;
+        CUDA_TRY(cudaMemcpyAsync(R.d_bar + 1, R.h_flag, sizeof(int32_t), cudaMemcpyHostToDevice, R.stream));
+    }
+    NCCL_TRY(n.GroupStart());
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        NCCL_TRY(n.AllReduce(R.d_bar + 1, R.d_bar + 1, 1, ncclInt32, ncclMin, R.comm, R.stream));
+    }
+    NCCL_TRY(n.GroupEnd());
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        CUDA_TRY(cudaMemcpyAsync(R.h_flag, R.d_bar + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, R.stream));
+    }
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        CUDA_TRY(cudaStreamSynchronize(R.stream));
+        if (*R.h_flag != 1) ok = false;
+    }
+    if (!ok) mg_win_close(m, mask);
+    *all_ok = ok;
+    return NUFFT_SUCCESS;
+}
+
+// my blocks -> the peers' windows, one copy-engine copy per peer (any alignment), staggered so that no receiver is the target of
+// every sender at once
+static int mg_put_all(Mgpu &m, MgRank &R, int w, const void *send, const std::vector<int64_t> &scnt, const std::vector<int64_t> &soff,
+                      const std::vector<int64_t> &doff, size_t esize)
+{
+    const int G = m.nranks;
+    for (int k = 0; k < G; ++k) {
+        const int r = (R.rank + k) % G;
+        if (scnt[r] <= 0) continue;
+        CUDA_TRY(cudaMemcpyAsync((char *)R.win[w][r] + (size_t)doff[r] * esize, (const char *)send + (size_t)soff[r] * esize, (size_t)scnt[r] * esize,
+                                 cudaMemcpyDefault, R.stream));
+    }
+    return NUFFT_SUCCESS;
+}
+
+// block copies into the peers' windows in one launch (16-byte units; anything else goes through cudaMemcpyAsync)
+struct CopyList {
+    CopyJobs j{};
+    int n = 0;
+    bool aligned = true;
+    void add(void *dst, const void *src, size_t bytes)
+    {
+        if (!bytes) return;
+        if (((uintptr_t)dst | (uintptr_t)src | bytes) & 15u) aligned = false;
+        j.dst[n] = (uint4 *)dst; j.src[n] = (const uint4 *)src; j.n16[n] = bytes / 16;
+        ++n;
+    }
+};
+static int mg_copy_run(MgRank &R, const CopyList &c)
+{
+    if (!c.n) return NUFFT_SUCCESS;
+    if (!c.aligned) {
+        for (int i = 0; i < c.n; ++i) CUDA_TRY(cudaMemcpyAsync(c.j.dst[i], c.j.src[i], (size_t)c.j.n16[i] * 16, cudaMemcpyDefault, R.stream));   // (never: sizes are powers of two)
+        return NUFFT_SUCCESS;
+    }
+    unsigned long long nmax = 0;
+    for (int i = 0; i < c.n; ++i) nmax = std::max(nmax, c.j.n16[i]);
+    const int sms = R.plan ? R.plan->num_sms : 148;
+    const unsigned gx = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(cdiv((int64_t)nmax, 1024), (unsigned long long)cdiv(4 * sms, c.n)));
+    mg_multi_copy_kernel<<<dim3(gx, (unsigned)c.n), 256, 0, R.stream>>>(c.j);
+    NUFFT_COUNT_LAUNCH();
+    return NUFFT_SUCCESS;
+}
+
+// all-to-all with per-peer element counts (bytes = count * esize) over NCCL, self part copied on the stream
 static int mg_alltoallv(Mgpu &m, MgRank &R, const void *send, const std::vector<int64_t> &scnt, const std::vector<int64_t> &soff, void *recv,
                         const std::vector<int64_t> &rcnt, const std::vector<int64_t> &roff, size_t esize)
 {
@@ -362,7 +630,6 @@ static int slab_set_points(Mgpu &m, const int64_t np[], const void *const x[])
         if (np[l] < 0 || np[l] >= ((int64_t)1 << 31) - 4096) { set_error("invalid number of points"); return NUFFT_ERR_ARG; }
         for (int d = 0; d < 3; ++d) if (np[l] > 0 && !x[3 * l + d]) { set_error("null point array"); return NUFFT_ERR_ARG; }
         mg_rec(R, 0);
-        NUFFT_TRY(mg_ensure_user(m, R, np[l]));
         CUDA_TRY(cudaMemsetAsync(R.d_cnt, 0, 2 * MG_MAX_RANKS * sizeof(unsigned long long), R.stream));
         if (np[l] > 0) {
             const unsigned grid = (unsigned)cdiv(np[l], MG_TILE);
@@ -384,25 +651,58 @@ static int slab_set_points(Mgpu &m, const int64_t np[], const void *const x[])
         CUDA_TRY(cudaSetDevice(R.dev));
         CUDA_TRY(cudaStreamSynchronize(R.stream));
     }
-    // (2) group the local points by destination, exchange the coordinates
+    // (2) counts and offsets of every exchange of this point set
     for (size_t l = 0; l < m.L.size(); ++l) {
         MgRank &R = m.L[l];
-        CUDA_TRY(cudaSetDevice(R.dev));
         R.sendcnt.assign(G, 0); R.sendoff.assign(G, 0); R.recvcnt.assign(G, 0); R.recvoff.assign(G, 0);
+        R.put_fwd.assign(G, 0); R.put_bwd.assign(G, 0);
         int64_t so = 0, ro = 0;
-        DestOffsets base{};
         for (int r = 0; r < G; ++r) {
             R.sendcnt[r] = (int64_t)R.h_cnt[(size_t)R.rank * MG_MAX_RANKS + r];
             R.recvcnt[r] = (int64_t)R.h_cnt[(size_t)r * MG_MAX_RANKS + R.rank];
             R.sendoff[r] = so; so += R.sendcnt[r];
             R.recvoff[r] = ro; ro += R.recvcnt[r];
-            base.off[r] = (unsigned long long)R.sendoff[r];
+            for (int t = 0; t < R.rank; ++t) {
+                R.put_fwd[r] += (int64_t)R.h_cnt[(size_t)t * MG_MAX_RANKS + r];        // senders before me in rank r's receive order
+                R.put_bwd[r] += (int64_t)R.h_cnt[(size_t)r * MG_MAX_RANKS + t];        // slabs before mine in rank r's send order
+            }
         }
         if (so != np[l]) { set_error("internal error: destination counts do not add up"); return NUFFT_ERR_STATE; }
         if (ro >= ((int64_t)1 << 31) - 4096) { set_error("too many points in one slab"); return NUFFT_ERR_UNSUPPORTED; }
         R.np_user = np[l];
         R.np_slab = ro;
-        NUFFT_TRY(mg_ensure_slab(m, R, ro));
+    }
+    // buffers: with peer windows a reallocation anywhere is a collective (the old mappings are closed before the owner frees)
+    bool remap = false;
+    if (m.p2p) {
+        const unsigned long long *cm = m.L[0].h_cnt;
+        for (int r = 0; r < G; ++r) {
+            int64_t row = 0, col = 0;
+            for (int t = 0; t < G; ++t) { row += (int64_t)cm[(size_t)r * MG_MAX_RANKS + t]; col += (int64_t)cm[(size_t)t * MG_MAX_RANKS + r]; }
+            if (row > m.cap_user_all[r]) { m.cap_user_all[r] = mg_grown(row); remap = true; }
+            if (col > m.cap_slab_all[r]) { m.cap_slab_all[r] = mg_grown(col); remap = true; }
+        }
+        if (remap) {
+            mg_win_close(m, W_DYNAMIC);
+            NUFFT_TRY(mg_host_barrier(m, 0));
+        }
+    }
+    for (auto &R : m.L) {
+        CUDA_TRY(cudaSetDevice(R.dev));
+        NUFFT_TRY(mg_ensure_user(m, R, R.np_user));
+        NUFFT_TRY(mg_ensure_slab(m, R, R.np_slab));
+    }
+    if (remap) {
+        bool ok = false;
+        NUFFT_TRY(mg_win_open(m, W_DYNAMIC, &ok));
+        if (!ok) { set_error("cannot map the peers' exchange buffers (CUDA IPC)"); return NUFFT_ERR_CUDA; }
+    }
+    // (3) group the local points by destination, exchange the coordinates
+    for (size_t l = 0; l < m.L.size(); ++l) {
+        MgRank &R = m.L[l];
+        CUDA_TRY(cudaSetDevice(R.dev));
+        DestOffsets base{};
+        for (int r = 0; r < G; ++r) base.off[r] = (unsigned long long)R.sendoff[r];
         if (np[l] > 0) {
             const unsigned grid = (unsigned)cdiv(np[l], MG_TILE);
             mg_dest_scatter_kernel<<<grid, 256, 0, R.stream>>>((const float *)x[3 * l], (const float *)x[3 * l + 1], (const float *)x[3 * l + 2], np[l],
@@ -411,14 +711,23 @@ static int slab_set_points(Mgpu &m, const int64_t np[], const void *const x[])
             NUFFT_COUNT_LAUNCH();
         }
     }
-    NCCL_TRY(n.GroupStart());
-    for (auto &R : m.L) {
-        CUDA_TRY(cudaSetDevice(R.dev));
-        for (int d = 0; d < 3; ++d)
-            NUFFT_TRY(mg_alltoallv(m, R, R.d_sx[d], R.sendcnt, R.sendoff, R.d_rx[d], R.recvcnt, R.recvoff, sizeof(float)));
+    if (m.p2p) {
+        NUFFT_TRY(mg_exchange_begin(m, 7u << W_RX0));
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            for (int d = 0; d < 3; ++d) NUFFT_TRY(mg_put_all(m, R, W_RX0 + d, R.d_sx[d], R.sendcnt, R.sendoff, R.put_fwd, sizeof(float)));
+        }
+        NUFFT_TRY(mg_exchange_end(m));
+    } else {
+        NCCL_TRY(n.GroupStart());
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            for (int d = 0; d < 3; ++d)
+                NUFFT_TRY(mg_alltoallv(m, R, R.d_sx[d], R.sendcnt, R.sendoff, R.d_rx[d], R.recvcnt, R.recvoff, sizeof(float)));
+        }
+        NCCL_TRY(n.GroupEnd());
     }
-    NCCL_TRY(n.GroupEnd());
-    // (3) bin the slab's points
+    // (4) bin the slab's points
     for (auto &R : m.L) {
         CUDA_TRY(cudaSetDevice(R.dev));
         mg_rec(R, 1);
@@ -426,6 +735,7 @@ static int slab_set_points(Mgpu &m, const int64_t np[], const void *const x[])
         NUFFT_TRY(binning_set_points(*R.plan, R.np_slab, rx));
         mg_rec(R, 2);
     }
+    m.busy |= 7u << W_RX0;
     CUDA_TRY(cudaGetLastError());
     return NUFFT_SUCCESS;
 }
@@ -445,13 +755,24 @@ static int slab_exchange_values(Mgpu &m, bool forward, const void *const vp_in[]
             }
         }
     }
-    NCCL_TRY(n.GroupStart());
-    for (auto &R : m.L) {
-        CUDA_TRY(cudaSetDevice(R.dev));
-        if (forward) NUFFT_TRY(mg_alltoallv(m, R, R.d_sv, R.sendcnt, R.sendoff, R.d_rv, R.recvcnt, R.recvoff, m.zbytes));
-        else NUFFT_TRY(mg_alltoallv(m, R, R.d_rv, R.recvcnt, R.recvoff, R.d_sv, R.sendcnt, R.sendoff, m.zbytes));
+    if (forward) m.busy |= 1u << W_SV;                 // the gather kernel writes d_sv
+    if (m.p2p) {
+        NUFFT_TRY(mg_exchange_begin(m, forward ? 1u << W_RV : 1u << W_SV));
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            if (forward) NUFFT_TRY(mg_put_all(m, R, W_RV, R.d_sv, R.sendcnt, R.sendoff, R.put_fwd, m.zbytes));
+            else NUFFT_TRY(mg_put_all(m, R, W_SV, R.d_rv, R.recvcnt, R.recvoff, R.put_bwd, m.zbytes));
+        }
+        NUFFT_TRY(mg_exchange_end(m));
+    } else {
+        NCCL_TRY(n.GroupStart());
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            if (forward) NUFFT_TRY(mg_alltoallv(m, R, R.d_sv, R.sendcnt, R.sendoff, R.d_rv, R.recvcnt, R.recvoff, m.zbytes));
+            else NUFFT_TRY(mg_alltoallv(m, R, R.d_rv, R.recvcnt, R.recvoff, R.d_sv, R.sendcnt, R.sendoff, m.zbytes));
+        }
+        NCCL_TRY(n.GroupEnd());
     }
-    NCCL_TRY(n.GroupEnd());
     if (!forward) {
         for (size_t l = 0; l < m.L.size(); ++l) {
             MgRank &R = m.L[l];
@@ -462,6 +783,7 @@ static int slab_exchange_values(Mgpu &m, bool forward, const void *const vp_in[]
                 NUFFT_COUNT_LAUNCH();
             }
         }
+        m.busy |= 1u << W_SV;                           // the scatter kernel reads d_sv
     }
     return NUFFT_SUCCESS;
 }
@@ -471,6 +793,22 @@ static int slab_transpose(Mgpu &m, bool forward)
 {
     NcclApi &n = nccl_api();
     const int G = m.nranks;
+    if (m.p2p) {
+        NUFFT_TRY(mg_exchange_begin(m, forward ? 1u << W_A : 1u << W_GRID));
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            const size_t blk = (size_t)(m.nk[0] * m.kyl * R.nz) * m.cbytes;
+            const char *src = (const char *)(forward ? R.plan->d_us : R.plan->d_pf_a);
+            CopyList c;
+            for (int k = 0; k < G; ++k) {
+                const int r = (R.rank + k) % G;
+                c.add((char *)R.win[forward ? W_A : W_GRID][r] + (size_t)R.rank * blk, src + (size_t)r * blk, blk);
+            }
+            NUFFT_TRY(mg_copy_run(R, c));
+        }
+        NUFFT_TRY(mg_exchange_end(m));
+        return NUFFT_SUCCESS;
+    }
     NCCL_TRY(n.GroupStart());
     for (auto &R : m.L) {
         CUDA_TRY(cudaSetDevice(R.dev));
@@ -503,8 +841,24 @@ static int slab_exec_type1(Mgpu &m, void *const uhat[], const void *const vp[])
         mg_rec(R, 5);
     }
     // halo planes -> neighbours: the M - 1 planes below the slab belong to rank - 1, the M planes above to rank + 1
-    NCCL_TRY(n.GroupStart());
+    m.busy |= (1u << W_RV) | (1u << W_GRID);            // spreading
+    if (m.p2p) {
+        NUFFT_TRY(mg_exchange_begin(m, 1u << W_HALO));
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            const int dn = (R.rank + G - 1) % G, up = (R.rank + 1) % G;
+            const char *grid = (const char *)R.plan->d_us;
+            const size_t lo_b = (size_t)(M - 1) * pl * m.zbytes, hi_b = (size_t)M * pl * m.zbytes;
+            CopyList c;
+            c.add((char *)R.win[W_HALO][dn], grid, lo_b);
+            c.add((char *)R.win[W_HALO][up] + lo_b, grid + (size_t)(M - 1 + R.nz) * pl * m.zbytes, hi_b);
+            NUFFT_TRY(mg_copy_run(R, c));
+        }
+        NUFFT_TRY(mg_exchange_end(m));
+    }
+    if (!m.p2p) NCCL_TRY(n.GroupStart());
     for (auto &R : m.L) {
+        if (m.p2p) break;
         CUDA_TRY(cudaSetDevice(R.dev));
         const int dn = (R.rank + G - 1) % G, up = (R.rank + 1) % G;
         char *grid = (char *)R.plan->d_us, *halo = (char *)R.d_halo;
@@ -514,7 +868,7 @@ static int slab_exec_type1(Mgpu &m, void *const uhat[], const void *const vp[])
         NCCL_TRY(n.Recv(halo, lo_b, ncclUint8, up, R.comm, R.stream));               // the upper neighbour's lower halo: my top planes
         NCCL_TRY(n.Recv(halo + lo_b, hi_b, ncclUint8, dn, R.comm, R.stream));        // the lower neighbour's upper halo: my first planes
     }
-    NCCL_TRY(n.GroupEnd());
+    if (!m.p2p) NCCL_TRY(n.GroupEnd());
     double nf = 1.0;
     for (int d = 0; d < 3; ++d) nf *= 2.0 * M_PI / (double)m.Nos[d];
     for (auto &R : m.L) {
@@ -534,7 +888,9 @@ static int slab_exec_type1(Mgpu &m, void *const uhat[], const void *const vp[])
         NUFFT_TRY(pfft_pass(p, 1, true, p.d_pf_a, p.d_us, m.nk[0], R.nz, 1.0, m.kyl, m.nk[0] * m.kyl * R.nz));
         mg_rec(R, 7);
     }
+    m.busy |= (1u << W_HALO) | (1u << W_A) | (1u << W_GRID);
     NUFFT_TRY(slab_transpose(m, true));
+    m.busy |= 1u << W_A;                                // the z pass reads the transposed intermediate
     for (size_t l = 0; l < m.L.size(); ++l) {
         MgRank &R = m.L[l];
         CUDA_TRY(cudaSetDevice(R.dev));
@@ -557,7 +913,9 @@ static int slab_exec_type2(Mgpu &m, void *const vp[], const void *const uhat[])
         NUFFT_TRY(pfft_pass(*R.plan, 2, false, uhat[l], R.plan->d_pf_a, m.nk[0] * m.kyl, 1, 1.0, 0, 0));
         mg_rec(R, 11);
     }
+    m.busy |= 1u << W_A;
     NUFFT_TRY(slab_transpose(m, false));
+    m.busy |= (1u << W_GRID) | (1u << W_A);             // the y and x passes
     for (auto &R : m.L) {
         CUDA_TRY(cudaSetDevice(R.dev));
         mg_rec(R, 12);
@@ -570,8 +928,23 @@ static int slab_exec_type2(Mgpu &m, void *const vp[], const void *const uhat[])
         mg_rec(R, 13);
     }
     // halo planes <- neighbours: my lower halo = the last M - 1 owned planes of rank - 1, my upper halo = the first M of rank + 1
-    NCCL_TRY(n.GroupStart());
+    if (m.p2p) {
+        NUFFT_TRY(mg_exchange_begin(m, 1u << W_GRID));
+        for (auto &R : m.L) {
+            CUDA_TRY(cudaSetDevice(R.dev));
+            const int dn = (R.rank + G - 1) % G, up = (R.rank + 1) % G;
+            const char *grid = (const char *)R.plan->d_us;
+            const size_t lo_b = (size_t)(M - 1) * pl * m.zbytes, hi_b = (size_t)M * pl * m.zbytes;
+            CopyList c;
+            c.add((char *)R.win[W_GRID][up], grid + (size_t)R.nz * pl * m.zbytes, lo_b);
+            c.add((char *)R.win[W_GRID][dn] + (size_t)(M - 1 + R.nz) * pl * m.zbytes, grid + (size_t)(M - 1) * pl * m.zbytes, hi_b);
+            NUFFT_TRY(mg_copy_run(R, c));
+        }
+        NUFFT_TRY(mg_exchange_end(m));
+    }
+    if (!m.p2p) NCCL_TRY(n.GroupStart());
     for (auto &R : m.L) {
+        if (m.p2p) break;
         CUDA_TRY(cudaSetDevice(R.dev));
         const int dn = (R.rank + G - 1) % G, up = (R.rank + 1) % G;
         char *grid = (char *)R.plan->d_us;
@@ -581,7 +954,7 @@ static int slab_exec_type2(Mgpu &m, void *const vp[], const void *const uhat[])
         NCCL_TRY(n.Recv(grid, lo_b, ncclUint8, dn, R.comm, R.stream));
         NCCL_TRY(n.Recv(grid + (size_t)(M - 1 + R.nz) * pl * m.zbytes, hi_b, ncclUint8, up, R.comm, R.stream));
     }
-    NCCL_TRY(n.GroupEnd());
+    if (!m.p2p) NCCL_TRY(n.GroupEnd());
     for (auto &R : m.L) {
         CUDA_TRY(cudaSetDevice(R.dev));
         mg_rec(R, 14);
@@ -589,6 +962,7 @@ static int slab_exec_type2(Mgpu &m, void *const vp[], const void *const uhat[])
         NUFFT_TRY(interp_run(*R.plan, rv, nullptr));
         mg_rec(R, 15);
     }
+    m.busy |= (1u << W_GRID) | (1u << W_RV);
     NUFFT_TRY(slab_exchange_values(m, false, nullptr, vp));
     for (auto &R : m.L) { CUDA_TRY(cudaSetDevice(R.dev)); mg_rec(R, 16); }
     return NUFFT_SUCCESS;
@@ -720,7 +1094,11 @@ int nufft_mgpu_create(nufft_mgpu *out, const nufft_opts *opts, int32_t nranks, i
             m->kyl = (int)(p->nk[1] / nranks);
             if (cudaMalloc(&R.d_cnt, (size_t)(2 + MG_MAX_RANKS) * MG_MAX_RANKS * sizeof(unsigned long long)) != cudaSuccess ||
                 cudaMallocHost(&R.h_cnt, (size_t)MG_MAX_RANKS * MG_MAX_RANKS * sizeof(unsigned long long)) != cudaSuccess ||
-                cudaMalloc(&R.d_halo, (size_t)(2 * p->M - 1) * p->Nos[0] * p->Nos[1] * m->zbytes) != cudaSuccess) {
+                cudaMalloc(&R.d_halo, (size_t)(2 * p->M - 1) * p->Nos[0] * p->Nos[1] * m->zbytes) != cudaSuccess ||
+                cudaMalloc(&R.d_msg, (size_t)(1 + MG_MAX_RANKS) * sizeof(WinMsg)) != cudaSuccess ||
+                cudaMallocHost(&R.h_msg, (size_t)(1 + MG_MAX_RANKS) * sizeof(WinMsg)) != cudaSuccess ||
+                cudaMalloc(&R.d_bar, 4 * sizeof(int32_t)) != cudaSuccess || cudaMemset(R.d_bar, 0, 4 * sizeof(int32_t)) != cudaSuccess ||
+                cudaMallocHost(&R.h_flag, 64) != cudaSuccess) {
                 cudaGetLastError();
                 set_error("cannot allocate the exchange buffers");
                 return fail(NUFFT_ERR_ALLOC);
@@ -731,6 +1109,31 @@ int nufft_mgpu_create(nufft_mgpu *out, const nufft_opts *opts, int32_t nranks, i
             R.ev_ok = true;
         }
     }
+    // z-slab exchanges through peer windows (NUFFT_B200_MGPU_P2P=0: NCCL send / recv): every GPU must reach every other one
+    if (strat == NUFFT_MGPU_SLAB) {
+        const char *e = getenv("NUFFT_B200_MGPU_P2P");
+        bool want = !(e && atoi(e) == 0);
+        if (want && nlocal > 1) {
+            for (auto &R : m->L) {
+                cudaSetDevice(R.dev);
+                for (auto &Q : m->L) {
+                    if (Q.dev == R.dev) continue;
+                    int can = 0;
+                    if (cudaDeviceCanAccessPeer(&can, R.dev, Q.dev) != cudaSuccess || !can) { cudaGetLastError(); want = false; continue; }
+                    const cudaError_t pe = cudaDeviceEnablePeerAccess(Q.dev, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) want = false;
+                    cudaGetLastError();
+                }
+            }
+        }
+        // a collective decision: mg_win_open agrees on it
+        m->cap_slab_all.assign(nranks, 0);
+        m->cap_user_all.assign(nranks, 0);
+        bool ok = false;
+        const int rc = mg_win_open(*m, W_STATIC, &ok, !want);
+        if (rc != NUFFT_SUCCESS) return fail(rc);
+        m->p2p = ok;
+    }
     *out = reinterpret_cast<nufft_mgpu>(m);
     return NUFFT_SUCCESS;
 }
@@ -740,6 +1143,13 @@ int nufft_mgpu_destroy(nufft_mgpu h)
     MgDeviceRestore restore_device;
     if (!h) return NUFFT_SUCCESS;
     Mgpu *m = reinterpret_cast<Mgpu *>(h);
+    if (m->p2p) {
+        // the peers' mappings of my buffers must be closed before I free them: close mine, then wait (bounded) for everybody
+        for (auto &R : m->L) { cudaSetDevice(R.dev); cudaStreamSynchronize(R.stream); }
+        mg_win_close(*m, W_DYNAMIC | W_STATIC);
+        mg_host_barrier(*m, 5.0);
+        cudaGetLastError();
+    }
     for (auto &R : m->L) mg_free_rank(R);
     delete m;
     return NUFFT_SUCCESS;
@@ -929,6 +1339,14 @@ int nufft_mgpu_get_stream(nufft_mgpu h, int32_t l, void **stream)
     Mgpu &m = *reinterpret_cast<Mgpu *>(h);
     if (l < 0 || l >= (int)m.L.size() || !stream) { set_error("invalid argument"); return NUFFT_ERR_ARG; }
     *stream = (void *)m.L[l].stream;
+    return NUFFT_SUCCESS;
+}
+
+int nufft_mgpu_exchange_mode(nufft_mgpu h, int32_t *mode)
+{
+    NUFFT_TRY(mg_check(h));
+    if (!mode) { set_error("null argument"); return NUFFT_ERR_ARG; }
+    *mode = reinterpret_cast<Mgpu *>(h)->p2p ? 1 : 0;
     return NUFFT_SUCCESS;
 }
 

@@ -52,6 +52,14 @@ static bool grid_tensor_map(Plan &p, CUtensorMap *out)
     return true;
 }
 
+// points per work item: a z segment of <= 128 planes holds ~ 256 points per column at the headline density, and an item that
+// spans more than one column pays a second window set-up (profiles/r2_ring_segment_chunk_sweep.txt: 3.09 -> 2.83 ms)
+static int ring_chunk(const Plan &p)
+{
+    if (getenv("NUFFT_B200_CS_CHUNK")) return cs::chunk_points();
+    return p.geom.B[2] <= 128 ? 256 : cs::chunk_points();
+}
+
 template <bool TMA>
 static int ring_spread_go(Plan &p, const CUtensorMap &tm, const KernelParams<float> &kp, const PtrPack &pack, int cn, float2 *us, const float *nuw,
                           int zlo, int nzwrap)
@@ -63,7 +71,7 @@ static int ring_spread_go(Plan &p, const CUtensorMap &tm, const KernelParams<flo
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[p.device & 63] = true;
     }
-    kern<<<p.num_sms, 32 * ring::NWARP, smem, p.stream>>>(tm, kp, p.geom, (int)p.Np, cs::chunk_points(), p.d_perm, p.d_counters,
+    kern<<<p.num_sms, 32 * ring::NWARP, smem, p.stream>>>(tm, kp, p.geom, (int)p.Np, ring_chunk(p), p.d_perm, p.d_counters,
                                                           (const float4 *)p.d_rec, pack, cn, us, p.ncells, nuw, zlo, nzwrap, p.nz_local);
     NUFFT_COUNT_LAUNCH();
     return NUFFT_SUCCESS;
@@ -91,7 +99,7 @@ static int ring_interp_go(Plan &p, const CUtensorMap &tm, const KernelParams<flo
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[p.device & 63] = true;
     }
-    kern<<<p.num_sms, 32 * ring::NWARP, smem, p.stream>>>(tm, kp, p.geom, (int)p.Np, cs::chunk_points(), p.d_perm, p.d_counters,
+    kern<<<p.num_sms, 32 * ring::NWARP, smem, p.stream>>>(tm, kp, p.geom, (int)p.Np, ring_chunk(p), p.d_perm, p.d_counters,
                                                           (const float4 *)p.d_rec, pack, cn, us, p.ncells, prefactor, nuw, zlo, nzwrap,
                                                           p.nz_local);
     NUFFT_COUNT_LAUNCH();

@@ -178,6 +178,13 @@ class MultiGPUPlan:
     def synchronize(self) -> None:
         _check(self._lib.nufft_mgpu_synchronize(self._h))
 
+    @property
+    def exchange(self) -> str:
+        """How the z-slab exchanges travel: "peer-windows" (direct copies into the receiver's buffers) or "nccl"."""
+        mode = C.c_int32(0)
+        _check(self._lib.nufft_mgpu_exchange_mode(self._h, C.byref(mode)))
+        return "peer-windows" if mode.value == 1 else "nccl"
+
     def timings(self, l: int = 0) -> dict:
         ms = (C.c_float * 16)()
         _check(self._lib.nufft_mgpu_get_timings(self._h, l, ms))

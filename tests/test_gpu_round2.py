@@ -239,6 +239,56 @@ def test_multi_gpu_transform_sharding_float64(nufft):
     assert mgpu_check.check(2, 32, 20000, "points", dtype=torch.complex128)
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_multi_gpu_slab_exchange_modes_and_growing_point_sets(nufft, p2p, monkeypatch):
+    """The z-slab exchanges through peer windows (default) and through NCCL send / recv (NUFFT_B200_MGPU_P2P=0) give the
+    single-GPU result; point sets that GROW between set_points calls force the collective reallocation (windows closed,
+    buffers reallocated, windows republished), repeated transforms on one point set reuse the mappings."""
+    _need_gpus(2)
+    import torch
+    monkeypatch.setenv("NUFFT_B200_MGPU_P2P", p2p)
+    G = 2
+    N = 64
+    kw = dict(kernel=nufft.BackwardsKaiserBesselKernel(), kernel_evalmode=nufft.FastApproximation())
+    mp = nufft.MultiGPUPlan(torch.complex64, (N, N, N), devices=list(range(G)), strategy="slab", **kw)
+    plan1 = nufft.PlanNUFFT(torch.complex64, (N, N, N), device="cuda:0", **kw)
+    try:
+        assert mp.exchange == ("peer-windows" if p2p == "1" else "nccl")
+        for it, n_loc in enumerate((3000, 40000, 40000, 90000, 500)):
+            pts, vals, outs, back = [], [], [], []
+            for g in range(G):
+                dev = f"cuda:{g}"
+                gen = torch.Generator(device=dev); gen.manual_seed(7 + 13 * g + it)
+                n = n_loc + 17 * g
+                pts.append(tuple(torch.rand(n, device=dev, generator=gen) * (2 * np.pi) for _ in range(3)))
+                vals.append(torch.view_as_complex(torch.randn(n, 2, device=dev, generator=gen)))
+                outs.append(torch.zeros(mp.local_shape(g), dtype=torch.complex64, device=dev))
+                back.append(torch.zeros(n, dtype=torch.complex64, device=dev))
+            for g in range(G):
+                torch.cuda.synchronize(g)
+            mp.set_points(pts)
+            for rep in range(2):
+                mp.exec_type1(outs, vals)
+            mp.synchronize()
+            full = mp.gather_output(outs)[0]
+            mp.synchronize()
+            plan1.set_points(tuple(torch.cat([p[d].to("cuda:0") for p in pts]) for d in range(3)))
+            ref = torch.empty(plan1.shape, dtype=torch.complex64, device="cuda:0")
+            plan1.exec_type1(ref, torch.cat([v.to("cuda:0") for v in vals]))
+            torch.cuda.synchronize(0)
+            assert l2_error(full.cpu().numpy(), ref.cpu().numpy()) <= 1e-5, (it, p2p)
+            for rep in range(2):
+                mp.exec_type2(back, outs)
+            mp.synchronize()
+            ref2 = torch.empty(sum(v.numel() for v in vals), dtype=torch.complex64, device="cuda:0")
+            plan1.exec_type2(ref2, full.to("cuda:0"))
+            torch.cuda.synchronize(0)
+            got = torch.cat([b.to("cuda:0") for b in back])
+            assert l2_error(got.cpu().numpy(), ref2.cpu().numpy()) <= 1e-5, (it, p2p)
+    finally:
+        mp.close(); plan1.close()
+
+
 def test_multi_gpu_single_rank_handle(nufft):
     """nranks = 1 needs neither NCCL nor a second device: the handle degenerates to the single-GPU plan."""
     import torch

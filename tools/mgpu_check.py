@@ -56,7 +56,7 @@ def check(G, modes, npts, strategy, dist="uniform", C=1, dtype=torch.complex64):
     mp.exec_type1([o if C > 1 else o[0] for o in out] if G > 1 else (out[0] if C > 1 else out[0][0]),
                   [v if C > 1 else v[0] for v in vloc] if G > 1 else (vloc[0] if C > 1 else vloc[0][0]))
     mp.synchronize()
-    res = {"strategy": mp.strategy, "G": G, "modes": modes, "np": npts, "dist": dist, "C": C}
+    res = {"strategy": mp.strategy, "G": G, "modes": modes, "np": npts, "dist": dist, "C": C, "exchange": mp.exchange}
     if mp.strategy == "slab":
         full = mp.gather_output([o[0] for o in out] if G > 1 else out[0][0])
         full = full if G > 1 else [full]
@@ -127,6 +127,7 @@ def timing(G, modes, npts, iters):
     ms = (time.perf_counter() - t0) / iters * 1e3
     stages = plan.timings(0) if G > 1 else dict(plan.timer)
     print(json.dumps({"G": G, "modes": modes, "np_total": n_loc * G, "ms_per_step": ms, "points_per_s": 2.0 * n_loc * G / (ms * 1e-3),
+                      "exchange": plan.exchange if G > 1 else None,
                       "stage_ms_rank0": {k: round(v, 3) for k, v in stages.items()}}), flush=True)
     plan.close()
 
@@ -139,6 +140,7 @@ if __name__ == "__main__":
     ap.add_argument("--time-modes", type=int, default=0)
     ap.add_argument("--time-np", type=int, default=0)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--skip-single", action="store_true", help="time the multi-GPU plan only")
     a = ap.parse_args()
     ok = True
     if a.modes > 0:
@@ -148,7 +150,7 @@ if __name__ == "__main__":
         ok &= check(a.gpus, 32, 20000, "points", dtype=torch.complex128)
         ok &= check(a.gpus, 32, 20000, "transforms", C=3, dtype=torch.complex128)
     if a.time_modes:
-        for g in sorted({1, a.gpus}):
+        for g in ([a.gpus] if a.skip_single else sorted({1, a.gpus})):
             timing(g, a.time_modes, a.time_np, a.iters)
     print("MGPU_CHECK", "ok" if ok else "FAILED")
     sys.exit(0 if ok else 1)
