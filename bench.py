@@ -641,15 +641,19 @@ def run_ours(args):
     B_2 = N_MODES ** 3 * 8 + 4 * G_x + npts * 24
     traffic = None                  # measured DRAM bytes per launch of that kernel (ncu --set full capture, profiles/)
     try:
-        t = json.loads((ROOT / "profiles" / "r1_dominant_kernel_traffic.json").read_text())[f"K-{dom}"]
+        t = json.loads((ROOT / "profiles" / "r2_dominant_kernel_traffic.json").read_text())[f"K-{dom}"]
         traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": f"K-{dom}", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": dom_bytes, "peak_source": peak_src,
-            "note": "column-streaming kernels (cs_spread.cuh / cs_interp.cuh): not HBM-bound at one point per 8 fine cells — LSU "
-                    "wavefronts 66-72 %, FMA pipe 48-56 %, issue slots 59-67 % of peak in the ncu captures "
-                    "(profiles/r1_cs_*_ncu_details.txt); see DESIGN.md section 3",
+            "note": "ring-window register kernels (ring_spread.cuh / ring_interp.cuh): not HBM-bound at one point per 8 fine cells — "
+                    "interpolation: L1/LSU busy 77 %, issue slots 63 %, FMA pipe 43 %, DRAM 23 % of peak; spreading: bound by the "
+                    "per-lane L2 reductions (0.99 ms without them, 2.79 ms with), issue slots 64 %, DRAM 32 % "
+                    "(profiles/r2_ring_interp_ncu_details.txt, r2b_ring_spread_ncu_details.txt, r2_spread_red_experiments.txt); "
+                    "measured DRAM traffic is 3.8 x (interpolation) / 5.3 x (spreading) the algorithmic bytes: neighbouring 4x4-cell "
+                    "columns re-read / re-reduce the overlapping part of their 11x11-cell windows (7.6 x the grid in total) and L2 "
+                    "catches about half of it (hit rate 43-50 %); see DESIGN.md section 3",
             "launch_ms": dom_ms,
             "type1_incl_set_points_frac": (B_1 + B_sp) / (ms_t1 * 1e-3) / 1e9 / peak,
             "type2_incl_set_points_frac": (B_2 + B_sp) / (ms_t2 * 1e-3) / 1e9 / peak,
