@@ -51,7 +51,12 @@ enum {
 enum { NUFFT_F32 = 0, NUFFT_F64 = 1 };
 /* src/NonuniformFFTs.jl:23-35: the four reference kernels */
 enum { NUFFT_KERNEL_KAISER_BESSEL = 0, NUFFT_KERNEL_BACKWARDS_KAISER_BESSEL = 1,
-       NUFFT_KERNEL_GAUSSIAN = 2, NUFFT_KERNEL_BSPLINE = 3 };
+       NUFFT_KERNEL_GAUSSIAN = 2, NUFFT_KERNEL_BSPLINE = 3,
+       /* NOT in the reference (src/Kernels/ has the four above): "exponential of semicircle" exp(beta (sqrt(1 - y^2) - 1)) of
+        * Barnett, Magland & af Klinteberg (2019), beta = 0.976 pi M (2 - 1/sigma), NUFFT_EVAL_FAST only (the same piecewise
+        * polynomials as KB / BKB), Fourier transform by Gauss-Legendre quadrature.  PARITY UNPINNED: there is no reference
+        * output to compare with; the oracle restates the same construction and both are checked against exact NUDFT sums. */
+       NUFFT_KERNEL_ES = 4 };
 /* src/Kernels/Kernels.jl:14-46 */
 enum { NUFFT_EVAL_FAST = 0, NUFFT_EVAL_DIRECT = 1 };
 /* gpu_method keyword, src/plan.jl:479, src/blocking/gpu.jl:26 */
@@ -120,6 +125,13 @@ int  nufft_plan_shape(nufft_plan plan, int64_t size_out[3], int64_t os_dims[3], 
  * coefficients [p][j] and the Fourier coefficients phihat_d (src/Kernels/*.jl). Host output. */
 int  nufft_plan_kernel_info(nufft_plan plan, int32_t d, double *shape_param, double *dx,
                             double *cs_host /* (M+4)*2M or NULL */, double *phihat_host /* size(p)[d] or NULL */);
+
+/* The same kernel data WITHOUT a plan and without touching a device: what a plan created from `opts` would hold for dimension d
+ * (optimal_kernel + the *KernelData constructors, src/Kernels/*.jl; phihat over the kept wavenumbers, src/plan.jl:503-512).
+ * cs_len >= (M+4)*2M, phihat_len >= size(p)[d]; any output pointer may be NULL.  Lets CPU-only tests compare the library's tables
+ * with the oracle's. */
+int  nufft_kernel_tables(const nufft_opts *opts, int32_t d, double *shape_param, double *dx, int64_t *os_dim,
+                         double *cs_host, size_t cs_len, double *phihat_host, size_t phihat_len);
 
 /* ---- set_points!(p, (xs, ys, zs)): src/set_points.jl:33-52 + src/blocking/gpu.jl:73-142 ---- */
 int  nufft_set_points(nufft_plan plan, int64_t np, const void *const x[/*dim*/]);

@@ -16,7 +16,7 @@ NUFFT_SUCCESS = 0
 NUFFT_ERR_ARG, NUFFT_ERR_DIM, NUFFT_ERR_UNSUPPORTED, NUFFT_ERR_CUDA = -1, -2, -3, -4
 NUFFT_ERR_CUFFT, NUFFT_ERR_ALLOC, NUFFT_ERR_STATE = -5, -6, -7
 NUFFT_F32, NUFFT_F64 = 0, 1
-KERNEL_IDS = {"kaiser_bessel": 0, "backwards_kaiser_bessel": 1, "gaussian": 2, "bspline": 3}
+KERNEL_IDS = {"kaiser_bessel": 0, "backwards_kaiser_bessel": 1, "gaussian": 2, "bspline": 3, "es": 4}
 EVAL_IDS = {"fast": 0, "direct": 1}
 METHOD_IDS = {"auto": 0, "global_memory": 1, "shared_memory": 2}
 
@@ -66,6 +66,8 @@ SYMBOLS = {
     "nufft_plan_destroy": (C.c_int, [_VP]),
     "nufft_plan_shape": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "nufft_plan_kernel_info": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), _VP, _VP]),
+    "nufft_kernel_tables": (C.c_int, [C.POINTER(nufft_opts), C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                      _VP, C.c_size_t, _VP, C.c_size_t]),
     "nufft_set_points": (C.c_int, [_VP, C.c_int64, _PP]),
     "nufft_set_points_matrix": (C.c_int, [_VP, C.c_int64, _VP]),
     "nufft_get_binning": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

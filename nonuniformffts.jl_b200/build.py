@@ -41,6 +41,7 @@ for t in ("float", "double"):
 
 
 import re
+import time
 
 _INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
 
@@ -79,6 +80,7 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
     if LIB.exists() and not force and LIB.stat().st_mtime >= _deps_mtime():
         return LIB
     OBJ.mkdir(exist_ok=True)
+    started = time.time()
     jobs = jobs or min(len(UNITS), os.cpu_count() or 4)
     stamp = OBJ / "flags.stamp"
     if not stamp.exists() or stamp.read_text() != _flags_stamp():
@@ -105,6 +107,8 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = False) -
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    if _deps_mtime() > started:          # a source changed while this build ran: the next call must look again
+        os.utime(LIB, (started, started))
     return LIB
 
 

@@ -76,6 +76,11 @@ static int check_exec(Plan &p, const void *const a[], const void *const b[])
 
 }  // namespace nufft
 
+namespace nufft {
+int host_kernel_tables(const nufft_opts &o, int d, double *shape, double *dx, int64_t *os_dim, double *cs, size_t cs_len, double *phihat,
+                       size_t phihat_len);          // host_plan.cu
+}
+
 using namespace nufft;
 
 extern "C" {
@@ -175,6 +180,14 @@ int nufft_plan_kernel_info(nufft_plan h, int32_t d, double *shape_param, double 
         else for (int64_t i = 0; i < p.nk[d]; ++i) phihat_host[i] = (double)((const float *)p.h_phihat[d].data())[i];
     }
     return NUFFT_SUCCESS;
+}
+
+int nufft_kernel_tables(const nufft_opts *opts, int32_t d, double *shape_param, double *dx, int64_t *os_dim, double *cs_host, size_t cs_len,
+                        double *phihat_host, size_t phihat_len)
+{
+    if (!opts) { set_error("null options"); return NUFFT_ERR_ARG; }
+    if (opts->struct_size != sizeof(nufft_opts)) { set_error("nufft_opts.struct_size does not match this library: ABI mismatch"); return NUFFT_ERR_ARG; }
+    return nufft::host_kernel_tables(*opts, d, shape_param, dx, os_dim, cs_host, cs_len, phihat_host, phihat_len);
 }
 
 int nufft_set_points(nufft_plan h, int64_t np, const void *const x[])
@@ -371,8 +384,8 @@ int nufft_describe(nufft_plan h, char *buf, size_t buflen)
     NUFFT_TRY(check_plan(h));
     Plan &p = *reinterpret_cast<Plan *>(h);
     if (!buf || buflen == 0) { set_error("null buffer"); return NUFFT_ERR_ARG; }
-    static const char *knames[] = {"KaiserBesselKernel", "BackwardsKaiserBesselKernel", "GaussianKernel", "BSplineKernel"};
-    const char *shape = (p.opts.kernel <= 1) ? "beta" : (p.opts.kernel == 2 ? "tau" : "-");
+    static const char *knames[] = {"KaiserBesselKernel", "BackwardsKaiserBesselKernel", "GaussianKernel", "BSplineKernel", "ESKernel"};
+    const char *shape = (p.opts.kernel <= 1 || p.opts.kernel == NUFFT_KERNEL_ES) ? "beta" : (p.opts.kernel == 2 ? "tau" : "-");
     double sigma = 0;
     for (int d = 0; d < p.D; ++d) sigma = std::fmax(sigma, (double)p.Nos[d] / (double)p.Ns[d]);
     const TileGeom &g = p.geom;

@@ -70,13 +70,41 @@ template <typename T> static void solve_vandermonde(int n, const T *xs, T *ys)
     }
 }
 
+// (NUFFT_KERNEL_ES is not in the reference: "exponential of semicircle" phi(y) = exp(beta (sqrt(1 - y^2) - 1)) of Barnett, Magland &
+// af Klinteberg, SIAM J. Sci. Comput. 41 (2019), beta = 0.976 pi M (2 - 1/sigma) = 2.30 x 2M at sigma = 2; evaluated through the
+// same piecewise polynomials as KB / BKB, Fourier transform by Gauss-Legendre quadrature.  Parity unpinned: see include/nufft_b200.h)
 static double kernel_fit_func(int kind, double beta, double y)
 {
     double z = 1.0 - y * y;
     double s = std::sqrt(z < 0 ? 0.0 : z);
     if (kind == NUFFT_KERNEL_KAISER_BESSEL) return std::cyl_bessel_i(0.0, beta * s);
+    if (kind == NUFFT_KERNEL_ES) return std::exp(beta * (s - 1.0));
     if (s == 0.0) return beta / M_PI;
     return std::sinh(beta * s) / (s * M_PI);
+}
+
+// Gauss-Legendre nodes and weights on [0, 1]: Newton iteration on the Legendre polynomial P_n
+static void gauss_legendre_unit(int n, std::vector<double> &x, std::vector<double> &w)
+{
+    x.assign(n, 0.0); w.assign(n, 0.0);
+    auto legendre = [n](double t, double &pn, double &pn1) {
+        double a = 1.0, b = t;
+        for (int k = 2; k <= n; ++k) { const double c = ((2.0 * k - 1.0) * t * b - (k - 1.0) * a) / k; a = b; b = c; }
+        pn = b; pn1 = a;
+    };
+    for (int i = 0; i < n; ++i) {
+        double t = std::cos(M_PI * (i + 0.75) / (n + 0.5)), pn, pn1;
+        for (int it = 0; it < 100; ++it) {
+            legendre(t, pn, pn1);
+            const double dt = pn / (n * (t * pn - pn1) / (t * t - 1.0));
+            t -= dt;
+            if (std::fabs(dt) < 1e-16) break;
+        }
+        legendre(t, pn, pn1);
+        const double dp = n * (t * pn - pn1) / (t * t - 1.0);
+        x[i] = 0.5 * (t + 1.0);
+        w[i] = 1.0 / ((1.0 - t * t) * dp * dp);
+    }
 }
 
 // Kernel data of one dimension in precision T: shape parameter, cs block, phihat table.
@@ -94,13 +122,13 @@ static void build_kernel_dim(Plan &p, int d, std::vector<T> &cs_block, std::vect
     T beta = 0, tau = 0;
     cs_block.assign((size_t)p.cs_stride, (T)0);
 
-    if (kind == NUFFT_KERNEL_KAISER_BESSEL || kind == NUFFT_KERNEL_BACKWARDS_KAISER_BESSEL) {
+    if (kind == NUFFT_KERNEL_KAISER_BESSEL || kind == NUFFT_KERNEL_BACKWARDS_KAISER_BESSEL || kind == NUFFT_KERNEL_ES) {
         if (user_param) beta = (T)p.opts.kernel_param;
         else {
             const T a = (T)M * ((T)2 - (T)1 / sigma_d);
             const double a2 = (double)(a * a);
             const double gamma = (kind == NUFFT_KERNEL_KAISER_BESSEL) ? std::sqrt(1.0 - 0.8 / a2)
-                                                                      : std::max(0.995, std::sqrt(1.0 - 0.3 / a2));
+                                 : (kind == NUFFT_KERNEL_BACKWARDS_KAISER_BESSEL) ? std::max(0.995, std::sqrt(1.0 - 0.3 / a2)) : 0.976;
             const T pa = (T)M_PI * a;
             beta = (T)((double)pa * gamma);
         }
@@ -147,6 +175,17 @@ static void build_kernel_dim(Plan &p, int d, std::vector<T> &cs_block, std::vect
     const int64_t nk = p.nk[d];
     const bool r2c = (!p.cplx) && d == 0;
     phihat.resize((size_t)nk);
+    // ES: phihat(k) = 2 w int_0^1 phi(y) cos(k w y) dy; with y = sin(theta) the integrand exp(beta (cos(theta) - 1)) cos(k w sin(theta))
+    // cos(theta) is entire (no square-root end point): 24 + 8 M Gauss-Legendre nodes on [0, pi/2] reach double precision
+    std::vector<double> qx, qw;
+    if (kind == NUFFT_KERNEL_ES) {
+        gauss_legendre_unit(24 + 8 * M, qx, qw);
+        for (size_t i = 0; i < qx.size(); ++i) {
+            const double th = 0.5 * M_PI * qx[i];
+            qw[i] *= 0.5 * M_PI * std::exp((double)beta * (std::cos(th) - 1.0)) * std::cos(th);
+            qx[i] = std::sin(th);
+        }
+    }
     for (int64_t a = 0; a < nk; ++a) {
         int64_t ki;
         if (r2c) ki = a;
@@ -158,7 +197,12 @@ static void build_kernel_dim(Plan &p, int d, std::vector<T> &cs_block, std::vect
         }
         const T k = (T)ki;
         T val;
-        if (kind == NUFFT_KERNEL_KAISER_BESSEL) {
+        if (kind == NUFFT_KERNEL_ES) {
+            const double kw = (double)k * (double)w;
+            double acc = 0.0;
+            for (size_t i = 0; i < qx.size(); ++i) acc += qw[i] * std::cos(kw * qx[i]);
+            val = (T)(2.0 * (double)w * acc);
+        } else if (kind == NUFFT_KERNEL_KAISER_BESSEL) {
             const T q = w * k;
             const T s = (T)std::sqrt((double)(beta * beta - q * q));
             val = (T)2 * w * (T)std::sinh((double)s) / s;
@@ -377,13 +421,18 @@ template <typename T> static int upload_tables(Plan &p)
     return NUFFT_SUCCESS;
 }
 
-int host_plan_init(Plan &p)
+// validation of the options and every size that follows from them (no device is touched)
+static int plan_sizes(Plan &p)
 {
     const nufft_opts &o = p.opts;
     if (o.dim < 1 || o.dim > 3) { set_error("dim must be 1, 2 or 3 (got %d)", o.dim); return NUFFT_ERR_ARG; }
     if (o.dtype != NUFFT_F32 && o.dtype != NUFFT_F64) { set_error("dtype must be NUFFT_F32 or NUFFT_F64"); return NUFFT_ERR_ARG; }
-    if (o.kernel < 0 || o.kernel > 3) { set_error("unknown kernel %d", o.kernel); return NUFFT_ERR_ARG; }
+    if (o.kernel < 0 || o.kernel > NUFFT_KERNEL_ES) { set_error("unknown kernel %d", o.kernel); return NUFFT_ERR_ARG; }
     if (o.eval_mode != NUFFT_EVAL_FAST && o.eval_mode != NUFFT_EVAL_DIRECT) { set_error("unknown eval_mode %d", o.eval_mode); return NUFFT_ERR_ARG; }
+    if (o.kernel == NUFFT_KERNEL_ES && o.eval_mode != NUFFT_EVAL_FAST) {
+        set_error("the ES kernel is evaluated through its piecewise polynomials only: use FastApproximation");
+        return NUFFT_ERR_UNSUPPORTED;
+    }
     if (o.ntransforms < 1) { set_error("ntransforms must be >= 1"); return NUFFT_ERR_ARG; }
     if (o.gpu_method < 0 || o.gpu_method > 2) { set_error("expected gpu_method in (auto, global_memory, shared_memory)"); return NUFFT_ERR_ARG; }
     if (o.half_support < MIN_M || o.half_support > MAX_M) {
@@ -395,10 +444,6 @@ int host_plan_init(Plan &p)
     p.D = o.dim; p.M = o.half_support; p.C = o.ntransforms;
     p.cplx = o.is_complex != 0; p.f64 = o.dtype == NUFFT_F64;
     p.real_bytes = p.f64 ? 8 : 4;
-    p.stream = (cudaStream_t)o.stream;
-    if (o.device >= 0) { CUDA_TRY(cudaSetDevice(o.device)); }
-    CUDA_TRY(cudaGetDevice(&p.device));
-    CUDA_TRY(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, p.device));
 
     // oversampled sizes (sigma converted to T first, src/plan.jl:575-576)
     for (int d = 0; d < p.D; ++d) {
@@ -435,6 +480,44 @@ int host_plan_init(Plan &p)
     p.nkept = p.nk[0] * p.nk[1] * p.nk[2];
     if (p.ncells >= ((int64_t)1 << 31)) { set_error("oversampled grid has >= 2^31 cells (32-bit cell indices)"); return NUFFT_ERR_UNSUPPORTED; }
     p.cs_stride = (p.M + 4) * 2 * p.M + p.M + I0_MAX_TERMS;
+    return NUFFT_SUCCESS;
+}
+
+// host-only: the kernel data of dimension d that a plan with these options would hold (nufft_kernel_tables)
+int host_kernel_tables(const nufft_opts &o, int d, double *shape, double *dx, int64_t *os_dim, double *cs, size_t cs_len, double *phihat,
+                       size_t phihat_len)
+{
+    Plan p;
+    p.opts = o;
+    NUFFT_TRY(plan_sizes(p));
+    if (d < 0 || d >= p.D) { set_error("dimension %d out of range", d); return NUFFT_ERR_ARG; }
+    const size_t ncs = (size_t)(p.M + 4) * 2 * p.M;
+    if ((cs && cs_len < ncs) || (phihat && phihat_len < (size_t)p.nk[d])) { set_error("output buffer too small"); return NUFFT_ERR_ARG; }
+    if (p.f64) {
+        std::vector<double> c, ph;
+        build_kernel_dim<double>(p, d, c, ph);
+        if (cs) std::copy(c.begin(), c.begin() + ncs, cs);
+        if (phihat) std::copy(ph.begin(), ph.end(), phihat);
+    } else {
+        std::vector<float> c, ph;
+        build_kernel_dim<float>(p, d, c, ph);
+        if (cs) for (size_t i = 0; i < ncs; ++i) cs[i] = (double)c[i];
+        if (phihat) for (size_t i = 0; i < ph.size(); ++i) phihat[i] = (double)ph[i];
+    }
+    if (shape) *shape = p.h_shape[d];
+    if (dx) *dx = p.h_dx[d];
+    if (os_dim) *os_dim = p.Nos[d];
+    return NUFFT_SUCCESS;
+}
+
+int host_plan_init(Plan &p)
+{
+    NUFFT_TRY(plan_sizes(p));
+    const nufft_opts &o = p.opts;
+    p.stream = (cudaStream_t)o.stream;
+    if (o.device >= 0) { CUDA_TRY(cudaSetDevice(o.device)); }
+    CUDA_TRY(cudaGetDevice(&p.device));
+    CUDA_TRY(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, p.device));
 
     NUFFT_TRY(p.f64 ? upload_tables<double>(p) : upload_tables<float>(p));
 

@@ -11,7 +11,7 @@
 module NonuniformFFTsB200
 
 export B200Plan, set_points!, exec_type1!, exec_type2!, HalfSupport,
-       KaiserBesselKernel, BackwardsKaiserBesselKernel, GaussianKernel, BSplineKernel
+       KaiserBesselKernel, BackwardsKaiserBesselKernel, GaussianKernel, BSplineKernel, ESKernel
 
 const libnufft = get(ENV, "NUFFT_B200_LIB", joinpath(@__DIR__, "..", "libnufft_b200.so"))
 
@@ -34,12 +34,14 @@ struct KaiserBesselKernel <: AbstractKernel; β::Float64; end
 struct BackwardsKaiserBesselKernel <: AbstractKernel; β::Float64; end
 struct GaussianKernel <: AbstractKernel; ℓ::Float64; end
 struct BSplineKernel <: AbstractKernel end
+struct ESKernel <: AbstractKernel; β::Float64; end     # not in the reference: exp(β (sqrt(1 - y^2) - 1)), FastApproximation only
 KaiserBesselKernel() = KaiserBesselKernel(NaN)
 BackwardsKaiserBesselKernel() = BackwardsKaiserBesselKernel(NaN)
 GaussianKernel() = GaussianKernel(NaN)
+ESKernel() = ESKernel(NaN)
 kernel_id(::KaiserBesselKernel) = Cint(0); kernel_id(::BackwardsKaiserBesselKernel) = Cint(1)
-kernel_id(::GaussianKernel) = Cint(2);     kernel_id(::BSplineKernel) = Cint(3)
-kernel_param(k::Union{KaiserBesselKernel, BackwardsKaiserBesselKernel}) = k.β
+kernel_id(::GaussianKernel) = Cint(2);     kernel_id(::BSplineKernel) = Cint(3); kernel_id(::ESKernel) = Cint(4)
+kernel_param(k::Union{KaiserBesselKernel, BackwardsKaiserBesselKernel, ESKernel}) = k.β
 kernel_param(k::GaussianKernel) = k.ℓ
 kernel_param(::BSplineKernel) = NaN
 

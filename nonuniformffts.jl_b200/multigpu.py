@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from .plan import (ArgumentError, Direct, KaiserBesselKernel, _CPLX, _KERNEL_BY_NAME, _REAL, _check, _to_torch_dtype, build_opts,
+from .plan import (ArgumentError, Direct, FastApproximation, KaiserBesselKernel, _CPLX, _KERNEL_BY_NAME, _REAL, _check, _to_torch_dtype, build_opts,
                    HalfSupport)
 
 
@@ -42,7 +42,7 @@ class MultiGPUPlan:
             kernel = KaiserBesselKernel()
         if isinstance(kernel, str):
             kernel = _KERNEL_BY_NAME[kernel]()
-        mode = kernel_evalmode if kernel_evalmode is not None else Direct()
+        mode = kernel_evalmode if kernel_evalmode is not None else (FastApproximation() if kernel.name == "es" else Direct())
         mode_name = mode if isinstance(mode, str) else mode.name
         if strategy not in _lib.MGPU_STRATEGIES:
             raise ArgumentError("expected strategy in (auto, slab, points, transforms)")

@@ -92,9 +92,21 @@ class BSplineKernel:
     param = None
 
 
+@dataclass(frozen=True)
+class ESKernel:
+    """"Exponential of semicircle" exp(beta (sqrt(1 - y^2) - 1)) (Barnett, Magland & af Klinteberg 2019).  NOT in the reference
+    (src/Kernels/ holds the four kernels above): parity unpinned, checked against exact sums.  FastApproximation only."""
+    beta: Optional[float] = None
+    name = "es"
+
+    @property
+    def param(self):
+        return self.beta
+
+
 _KERNEL_BY_NAME = {
     "kaiser_bessel": KaiserBesselKernel, "backwards_kaiser_bessel": BackwardsKaiserBesselKernel,
-    "gaussian": GaussianKernel, "bspline": BSplineKernel,
+    "gaussian": GaussianKernel, "bspline": BSplineKernel, "es": ESKernel,
 }
 
 
@@ -172,6 +184,28 @@ def build_opts(lib, dims, is_complex, real_dtype, M, sigma, kernel, mode_name, n
     return o
 
 
+def kernel_tables(dtype, dims, d: int = 0, m=4, sigma: float = 2.0, kernel=None, kernel_evalmode=None, fftshift: bool = False):
+    """Kernel data of dimension ``d`` that ``PlanNUFFT(dtype, dims, ...)`` would hold — computed by the library's host code without
+    a plan and without a GPU (``nufft_kernel_tables``): dict(shape, dx, os_dim, cs[(M+4), 2M], phihat[size(p)[d]])."""
+    import numpy as np
+    lib = _lib.load()
+    dtype = _to_torch_dtype(dtype)
+    real_dtype = _REAL[dtype]
+    dims = (int(dims),) if isinstance(dims, int) else tuple(int(n) for n in dims)
+    M = m.M if isinstance(m, HalfSupport) else int(m)
+    kernel = KaiserBesselKernel() if kernel is None else (_KERNEL_BY_NAME[kernel]() if isinstance(kernel, str) else kernel)
+    mode = kernel_evalmode if kernel_evalmode is not None else (FastApproximation() if kernel.name == "es" else Direct())
+    o = build_opts(lib, dims, dtype.is_complex, real_dtype, M, sigma, kernel, mode if isinstance(mode, str) else mode.name, 1, fftshift,
+                   False, "auto", None, 0, None, None, False, 0)
+    nk = dims[d] // 2 + 1 if (not dtype.is_complex and d == 0) else dims[d]
+    shape, dx, os_dim = C.c_double(), C.c_double(), C.c_int64()
+    cs = np.zeros((M + 4, 2 * M), dtype=np.float64)
+    ph = np.zeros(nk, dtype=np.float64)
+    _check(lib.nufft_kernel_tables(C.byref(o), d, C.byref(shape), C.byref(dx), C.byref(os_dim), cs.ctypes.data_as(C.c_void_p), cs.size,
+                                   ph.ctypes.data_as(C.c_void_p), ph.size))
+    return dict(shape=shape.value, dx=dx.value, os_dim=os_dim.value, cs=cs, phihat=ph)
+
+
 class PlanNUFFT:
     """PlanNUFFT([T = ComplexF64], dims; m = 4, sigma = 2, kernel, ntransforms = 1, fftshift = false, ...).
 
@@ -200,7 +234,7 @@ class PlanNUFFT:
             kernel = KaiserBesselKernel()
         if isinstance(kernel, str):
             kernel = _KERNEL_BY_NAME[kernel]()
-        mode = kernel_evalmode if kernel_evalmode is not None else Direct()
+        mode = kernel_evalmode if kernel_evalmode is not None else (FastApproximation() if kernel.name == "es" else Direct())
         mode_name = mode if isinstance(mode, str) else mode.name
         if gpu_method not in _lib.METHOD_IDS:
             raise ArgumentError("expected gpu_method in (auto, global_memory, shared_memory)")

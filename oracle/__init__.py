@@ -27,7 +27,8 @@ import scipy.fft as _sfft
 _HERE = Path(__file__).resolve().parent
 _LIB = None
 
-KERNELS = {"kaiser_bessel": 0, "backwards_kaiser_bessel": 1, "gaussian": 2, "bspline": 3}
+KERNELS = {"kaiser_bessel": 0, "backwards_kaiser_bessel": 1, "gaussian": 2, "bspline": 3,
+           "es": 4}          # "es": not in the reference (exponential of semicircle; parity unpinned, checked against exact sums)
 EVALMODES = {"fast": 0, "direct": 1}
 
 

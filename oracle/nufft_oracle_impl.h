@@ -26,7 +26,7 @@
 #define ORC_MAXP (ORC_MAXM + 4)
 
 typedef struct {
-    int kind;      /* 0 KB, 1 BKB, 2 Gaussian, 3 B-spline */
+    int kind;      /* 0 KB, 1 BKB, 2 Gaussian, 3 B-spline, 4 ES (not in the reference: parity unpinned, see orc_fit_func) */
     int M;         /* half support */
     int N;         /* oversampled grid size in this dimension */
     REAL beta;     /* KB / BKB shape parameter */
@@ -128,12 +128,18 @@ static void SUF(orc_solve_vandermonde)(int n, const REAL *xs, REAL *ys /* in: sa
  * KB  : kaiser_bessel.jl:127-131  besseli0(beta*sqrt(1-x^2))
  * BKB : kaiser_bessel_backwards.jl:98-102  sinh(beta*s)/(s*pi)
  * The fit samples are evaluated in Float64 (y = h + x*delta is Float64 in the reference
- * because h, delta are Float64 literals, piecewise_polynomial.jl:63-68) then rounded to T. */
+ * because h, delta are Float64 literals, piecewise_polynomial.jl:63-68) then rounded to T.
+ * ES  : NOT in the reference (the north star of this project names it; PARITY UNPINNED, checked against exact NUDFT sums only).
+ *       "Exponential of semicircle" of Barnett, Magland & af Klinteberg, SIAM J. Sci. Comput. 41 (2019):
+ *       phi(y) = exp(beta (sqrt(1 - y^2) - 1)),  beta = 0.976 pi M (2 - 1/sigma)  (= 2.30 x 2M at sigma = 2, their rule);
+ *       evaluated through the same piecewise polynomials as KB / BKB; its Fourier transform has no closed form and is
+ *       computed by Gauss-Legendre quadrature (orc_es_fourier). */
 static double SUF(orc_fit_func)(int kind, double beta, double y)
 {
     double z = 1.0 - y * y;
     double s = sqrt(z < 0 ? 0 : z);
     if (kind == 0) return orc_besseli0(beta * s);
+    if (kind == 4) return exp(beta * (s - 1.0));
     if (s == 0) return beta / M_PI;
     return sinh(beta * s) / (s * M_PI);
 }
@@ -168,17 +174,17 @@ static void SUF(orc_fit_piecewise)(SUF(orc_kernel) *g)
  */
 int SUF(orc_kernel_init)(SUF(orc_kernel) *g, int kind, int M, int64_t N, REAL sigma, double param)
 {
-    if (M < 1 || M > ORC_MAXM || kind < 0 || kind > 3) return -1;
+    if (M < 1 || M > ORC_MAXM || kind < 0 || kind > 4) return -1;
     memset(g, 0, sizeof(*g));
     g->kind = kind; g->M = M; g->N = (int)N;
     const REAL L = SUF(orc_period)();
     g->dx = L / (REAL)N;
     g->w = (REAL)M * g->dx;
-    if (kind == 0 || kind == 1) {
+    if (kind == 0 || kind == 1 || kind == 4) {
         if (isnan(param)) {
             REAL a = (REAL)M * ((REAL)2 - (REAL)1 / sigma);
             double a2 = (double)(a * a);
-            double gamma = (kind == 0) ? sqrt(1.0 - 0.8 / a2) : fmax(0.995, sqrt(1.0 - 0.3 / a2));
+            double gamma = (kind == 0) ? sqrt(1.0 - 0.8 / a2) : (kind == 1) ? fmax(0.995, sqrt(1.0 - 0.3 / a2)) : 0.976;
             REAL pa = (REAL)M_PI * a;
             g->beta = (REAL)((double)pa * gamma);
         } else {
@@ -202,8 +208,57 @@ int SUF(orc_kernel_init)(SUF(orc_kernel) *g, int kind, int M, int64_t N, REAL si
 
 /* evaluate_fourier_func: KB kaiser_bessel.jl:168-175; BKB kaiser_bessel_backwards.jl:138-145;
  * Gaussian gaussian.jl:117-122; B-spline bspline.jl:121-129.  (Kernels.jl:108-117 applies it to ks.) */
+/* Gauss-Legendre nodes and weights on [0, 1] (Newton iteration on P_n, double precision) */
+#ifndef ORC_GAUSS_LEGENDRE_DEFINED
+#define ORC_GAUSS_LEGENDRE_DEFINED
+static void orc_gauss_legendre01(int n, double *x, double *w)
+{
+    for (int i = 0; i < n; ++i) {
+        double t = cos(M_PI * (i + 0.75) / (n + 0.5)), dp = 1.0;
+        for (int it = 0; it < 100; ++it) {
+            double p0 = 1.0, p1 = t;
+            for (int k = 2; k <= n; ++k) { const double p2 = ((2.0 * k - 1.0) * t * p1 - (k - 1.0) * p0) / k; p0 = p1; p1 = p2; }
+            dp = n * (t * p1 - p0) / (t * t - 1.0);
+            const double dt = p1 / dp;
+            t -= dt;
+            if (fabs(dt) < 1e-16) break;
+        }
+        {   /* derivative at the converged node */
+            double p0 = 1.0, p1 = t;
+            for (int k = 2; k <= n; ++k) { const double p2 = ((2.0 * k - 1.0) * t * p1 - (k - 1.0) * p0) / k; p0 = p1; p1 = p2; }
+            dp = n * (t * p1 - p0) / (t * t - 1.0);
+        }
+        x[i] = 0.5 * (t + 1.0);
+        w[i] = 1.0 / ((1.0 - t * t) * dp * dp);          /* = (2 / ((1 - t^2) P_n'(t)^2)) / 2 for the interval [0, 1] */
+    }
+}
+#endif
+
+/* ES: phihat(k) = int_{-w}^{w} phi(x / w) exp(-i k x) dx = 2 w int_0^1 phi(y) cos(k w y) dy; with y = sin(theta) the integrand
+ * exp(beta (cos(theta) - 1)) cos(k w sin(theta)) cos(theta) is entire (no square-root end point): Gauss-Legendre on [0, pi/2]
+ * with 24 + 8 M nodes converges to double precision */
+static void SUF(orc_es_fourier)(const SUF(orc_kernel) *g, int64_t n, const REAL *ks, REAL *out)
+{
+    enum { QMAX = 24 + 8 * ORC_MAXM };
+    double x[QMAX], wq[QMAX], f[QMAX], sn[QMAX];
+    const int q = 24 + 8 * g->M;
+    orc_gauss_legendre01(q, x, wq);
+    for (int i = 0; i < q; ++i) {
+        const double th = 0.5 * M_PI * x[i];
+        sn[i] = sin(th);
+        f[i] = 0.5 * M_PI * wq[i] * exp((double)g->beta * (cos(th) - 1.0)) * cos(th);
+    }
+    for (int64_t a = 0; a < n; ++a) {
+        const double kw = (double)ks[a] * (double)g->w;
+        double acc = 0.0;
+        for (int i = 0; i < q; ++i) acc += f[i] * cos(kw * sn[i]);
+        out[a] = (REAL)(2.0 * (double)g->w * acc);
+    }
+}
+
 void SUF(orc_kernel_fourier)(const SUF(orc_kernel) *g, int64_t n, const REAL *ks, REAL *out)
 {
+    if (g->kind == 4) { SUF(orc_es_fourier)(g, n, ks, out); return; }
     for (int64_t a = 0; a < n; ++a) {
         REAL k = ks[a];
         if (g->kind == 0) {
@@ -263,7 +318,7 @@ int64_t SUF(orc_kernel_eval)(const SUF(orc_kernel) *g, int mode, REAL x, REAL *v
         return i;
     }
     if (mode == 0) {
-        if (g->kind == 0 || g->kind == 1) {
+        if (g->kind == 0 || g->kind == 1 || g->kind == 4) {
             REAL xt = (REAL)2 * X - (REAL)1;
             const int n = M + 4;
             for (int j = 0; j < W; ++j) {
@@ -295,6 +350,7 @@ int64_t SUF(orc_kernel_eval)(const SUF(orc_kernel) *g, int mode, REAL x, REAL *v
             REAL z = (REAL)1 - y * y;
             REAL s = (REAL)sqrt((double)(z < 0 ? 0 : z));
             if (g->kind == 0) vals[j - 1] = (REAL)orc_besseli0((double)(g->beta * s));
+            else if (g->kind == 4) vals[j - 1] = (REAL)exp((double)(g->beta * (s - (REAL)1)));
             else {
                 REAL bs = g->beta * s;
                 REAL f = (s == 0) ? (REAL)1 : (REAL)sinh((double)bs) / bs;

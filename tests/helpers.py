@@ -53,7 +53,7 @@ def make_values(rng, n, dtype):
 
 
 KERNEL_CLASSES = {"kaiser_bessel": "KaiserBesselKernel", "backwards_kaiser_bessel": "BackwardsKaiserBesselKernel",
-                  "gaussian": "GaussianKernel", "bspline": "BSplineKernel"}
+                  "gaussian": "GaussianKernel", "bspline": "BSplineKernel", "es": "ESKernel"}
 
 
 def gpu_plan(nufft, dtype, dims, *, m=4, sigma=2.0, kernel="backwards_kaiser_bessel", evalmode="fast",

@@ -30,6 +30,10 @@ def run_case(nufft, oracle_mod, dtype, dims, Np, *, m=4, sigma=2.0, kernel="back
     # kernel tables
     for d in range(D):
         ki = gp.kernel_info(d)
+        if kernel == "es":     # a quadrature sum: two builds may differ by an ulp of its LARGEST term, phihat(0)
+            np.testing.assert_allclose(ki["phihat"], op.phihat[d].astype(np.float64), rtol=0,
+                                       atol=50 * np.finfo(rt).eps * float(np.abs(op.phihat[d]).max()))
+            continue
         np.testing.assert_allclose(ki["phihat"], op.phihat[d].astype(np.float64), rtol=50 * np.finfo(rt).eps)
     # --- set_points!: exact binning parity
     op.set_points(xs)

@@ -208,6 +208,40 @@ def test_polynomial_tables_equal_the_oracle(nufft, oracle_mod, dtype, kernel):
         gp.close()
 
 
+# ---- the ES kernel (not in the reference: parity unpinned; the oracle restates the same construction) ----------------------------
+@pytest.mark.parametrize("dtype,dims,Np,M,sigma", [
+    (np.complex64, (35, 64, 40), 20000, 4, 2.0),          # ring-window kernels
+    (np.float32, (35, 64, 40), 20000, 4, 2.0),            # column-streaming kernels (real data)
+    (np.complex128, (64, 81), 5000, 4, 1.5),              # shared-memory tile kernels, cuFFT
+    (np.float64, (256,), 1000, 6, 2.0),
+])
+def test_es_kernel_against_oracle(nufft, oracle_mod, dtype, dims, Np, M, sigma):
+    """Tables (phihat by quadrature, polynomial coefficients), binning, type 1 and type 2 of an ES plan against the oracle."""
+    from test_gpu_parity import run_case
+    run_case(nufft, oracle_mod, dtype, dims, Np, m=M, sigma=sigma, kernel="es", evalmode="fast", seed=11)
+
+
+def test_es_kernel_exact_sums_and_errors(nufft, oracle_mod):
+    """Against exact NUDFT sums (the only absolute check an unpinned kernel has), and Direct evaluation is refused."""
+    import torch
+    rng = np.random.default_rng(12)
+    N, Np = 64, 400
+    x = (rng.random(Np) * 2 * np.pi)
+    v = make_values(rng, Np, np.complex128)
+    gp = gpu_plan(nufft, np.complex128, (N,), m=6, sigma=2.0, kernel="es")
+    gp.set_points((to_dev(x),))
+    u = torch.empty(gp.shape, dtype=torch.complex128, device="cuda")
+    gp.exec_type1(u, to_dev(v))
+    ks = [np.fft.fftfreq(N, 1 / N).astype(np.int64)]
+    assert l2_error(u.cpu().numpy(), oracle_mod.nudft_type1(ks, [x], v)) < 4 * 6 * 10.0 ** (-1.9 * 6)
+    gp.close()
+    with pytest.raises(nufft.ArgumentError):
+        nufft.PlanNUFFT(torch.complex64, (32, 32), kernel=nufft.ESKernel(), kernel_evalmode=nufft.Direct())
+    p = nufft.PlanNUFFT(torch.complex64, (32, 32), kernel=nufft.ESKernel())           # default mode of ESKernel: FastApproximation
+    assert "ESKernel" in repr(p)
+    p.close()
+
+
 # ---- multi-GPU strategies of the C ABI (nufft_mgpu_*), one process driving all devices ------------------------------------------
 def _need_gpus(n):
     import torch

@@ -14,6 +14,9 @@ independently in 50-digit arithmetic (mpmath) and the oracle's plan data must ag
                    in T; fast Gaussian gridding (gaussian.jl:125-192); de Boor recursion (bspline.jl:143-193) against the
                    closed-form cardinal B-spline
   direct evaluation  KB :198-210, BKB :158-175, Gaussian :141-153 from the definitions
+
+The ES kernel ("es": exponential of semicircle, NOT in the reference — parity unpinned) goes through the same checks against its
+own definition: beta = 0.976 pi M (2 - 1/sigma), phi(y) = exp(beta (sqrt(1 - y^2) - 1)), phihat by 50-digit quadrature.
 """
 import numpy as np
 import pytest
@@ -37,6 +40,8 @@ def shape_params(kernel, M, sigma_T):
         return mp.pi * a * mp.sqrt(1 - mp.mpf("0.8") / a ** 2), None
     if kernel == "backwards_kaiser_bessel":
         return mp.pi * a * max(mp.mpf("0.995"), mp.sqrt(1 - mp.mpf("0.3") / a ** 2)), None
+    if kernel == "es":
+        return mp.mpf("0.976") * mp.pi * a, None
     if kernel == "gaussian":
         return None, mp.sqrt(s * M / (2 * s - 1) / mp.pi)
     return None, None
@@ -53,6 +58,8 @@ def kernel_func(kernel, beta, tau, M, dx):
         return f
     if kernel == "gaussian":
         return lambda y: mp.exp(-((y * M * dx) ** 2) / tau)
+    if kernel == "es":
+        return lambda y: mp.exp(beta * (mp.sqrt(max(mp.mpf(0), 1 - y * y)) - 1))
     raise ValueError(kernel)
 
 
@@ -68,7 +75,7 @@ def cardinal_bspline(n, t):
     return s / mp.factorial(n - 1)
 
 
-CASES = [(T, k, M, sig) for T in (np.float64, np.float32) for k in ("kaiser_bessel", "backwards_kaiser_bessel", "gaussian", "bspline")
+CASES = [(T, k, M, sig) for T in (np.float64, np.float32) for k in ("kaiser_bessel", "backwards_kaiser_bessel", "gaussian", "bspline", "es")
          for M, sig in ((4, 2.0), (4, 1.5), (6, 1.25), (8, 2.0), (2, 2.0))]
 
 
@@ -103,16 +110,27 @@ def test_shape_and_fourier_tables(T, kernel, M, sigma):
             ref.append(w * mp.besseli(0, mp.sqrt(beta ** 2 - (w * k) ** 2)))
         elif kernel == "gaussian":
             ref.append(mp.exp(-tau * k ** 2 / 4) * mp.sqrt(mp.pi * tau))
+        elif kernel == "es":
+            if int(k) % 5 not in (0, 1) and abs(int(k)) != int(max(abs(ks))):
+                ref.append(None)                                  # (50-digit quadrature is slow: a subset of the wavenumbers)
+                continue
+            f = lambda y: mp.exp(beta * (mp.sqrt(1 - y * y) - 1)) * mp.cos(k * w * y)
+            ref.append(2 * w * mp.quad(f, mp.linspace(0, 1, 5)))
         else:
             kh = k * dx / 2
             ref.append(dx if k == 0 else (mp.sin(kh) / kh) ** (2 * M) * dx)
-    ref = np.array([float(r) for r in ref])
+    sel = np.array([r is not None for r in ref])
+    ref = np.array([float(r) for r in ref if r is not None])
     # relative error of phihat: a few ulp of T times the conditioning of sinh / I0 / exp at arguments of size beta (~ 2.3 M pi)
-    rel = np.abs(p.phihat[0].astype(np.float64) - ref) / np.abs(ref)
+    rel = np.abs(p.phihat[0].astype(np.float64)[sel] - ref) / np.abs(ref)
+    if kernel == "es":
+        # no closed form: the quadrature sum of an oscillatory integrand is accurate to a few ulp of its LARGEST value phihat(0),
+        # the cancellation at high k (phihat falls by 1e-3 ... 1e-6 across the kept band) is inherent in T
+        rel = np.abs(p.phihat[0].astype(np.float64)[sel] - ref) / np.abs(ref).max()
     assert rel.max() <= (60 + 8 * M * np.pi) * eps, rel.max() / eps
 
 
-@pytest.mark.parametrize("T,kernel,M,sigma", [c for c in CASES if c[1] in ("kaiser_bessel", "backwards_kaiser_bessel")])
+@pytest.mark.parametrize("T,kernel,M,sigma", [c for c in CASES if c[1] in ("kaiser_bessel", "backwards_kaiser_bessel", "es")])
 def test_piecewise_polynomial_is_the_chebyshev_interpolant(T, kernel, M, sigma):
     N = 48
     p = OraclePlan(T, N, m=M, sigma=sigma, kernel=kernel)
@@ -156,7 +174,12 @@ def test_piecewise_polynomial_is_the_chebyshev_interpolant(T, kernel, M, sigma):
     # (b) and the interpolant approximates the kernel to the accuracy the reference's own test demands at HalfSupport(4),
     #     sigma = 1.5 (test/approx_window_functions.jl:9-24, rtol = 1e-7 on the value vector); degree M + 3 = 5 at
     #     HalfSupport(2) reaches 1.2e-5, which is all a 1e-3-accurate M = 2 transform needs
-    assert worst_f <= (max(2e-7, 2.0 ** (M + 5) * eps) if M >= 4 else 2e-5), worst_f
+    bound = max(2e-7, 2.0 ** (M + 5) * eps) if M >= 4 else 2e-5
+    if kernel == "es":
+        # the ES kernel ends in a square root: on the outermost sub-intervals a polynomial misses it by ~ exp(-beta) sqrt(1/M)
+        # of the peak (4.9e-5 at M = 2, 4e-9 at M = 4) — the size of the kernel's own truncation error, as in FINUFFT
+        bound += 0.6 * float(mp.exp(-beta))
+    assert worst_f <= bound, worst_f
 
 
 @pytest.mark.parametrize("T,kernel,M,sigma", CASES)
@@ -167,7 +190,7 @@ def test_direct_and_gridding_evaluation(T, kernel, M, sigma):
     Nos = p.Nos[0]
     dx = TWO_PI / Nos
     eps = float(np.finfo(T).eps)
-    beta = mp.mpf(kd["beta"]) if kernel.endswith("bessel") else None
+    beta = mp.mpf(kd["beta"]) if kernel.endswith("bessel") or kernel == "es" else None
     tau = mp.mpf(kd["tau"]) if kernel == "gaussian" else None
     L = 2 * M
     for X in (0.001953125, 0.0625, 0.4375, 0.90625):
@@ -175,7 +198,7 @@ def test_direct_and_gridding_evaluation(T, kernel, M, sigma):
         x = T((cell + X) * float(dx))
         r = (mp.mpf(float(x)) / TWO_PI) * Nos
         for mode in ("direct", "fast"):
-            if mode == "fast" and kernel.endswith("bessel"):
+            if mode == "fast" and (kernel.endswith("bessel") or kernel == "es"):
                 continue                                           # covered by the interpolant test
             i, vals = p.evaluate_kernel(x, 0, mode=mode)
             Xe = r - (i - 1)
