@@ -452,6 +452,7 @@ def run_ours_multi(args, world, rank, local_rank):
             "cpu_baseline": None, "clocks": clocks,
             "e2e": {"value": pts_per_step * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K, "numa_node_rank0": numa,
+                    "h2d_gb_per_s": h2d * K / (ms_e2e * 1e-3) / 1e9, "d2h_gb_per_s": d2h * K / (ms_e2e * 1e-3) / 1e9,
                     "note": "public API (MultiGPUPlan) with pinned host buffers allocated on each GPU's NUMA node; per step every rank "
                             "copies its points+values+spectrum block in and both results out on copy streams, double-buffered"},
             "gpu_launches": int(launches),
@@ -715,8 +716,10 @@ def run_ours(args):
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / K,
+                    "h2d_gb_per_s": h2d * K / (ms_e2e * 1e-3) / 1e9, "d2h_gb_per_s": d2h * K / (ms_e2e * 1e-3) / 1e9,
                     "note": "public API with pinned host buffers; per-step H2D of points+values+spectrum and D2H of both "
-                            "results on copy streams, double-buffered and overlapped with the transforms"},
+                            "results on copy streams, double-buffered and overlapped with the transforms; when ms_per_step "
+                            "exceeds the device-resident step the sustained H2D rate (h2d_gb_per_s) is the bound: the host link"},
             "gpu_launches": int(launches),
         }
         print(json.dumps(line))
