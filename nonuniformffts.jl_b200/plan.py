@@ -197,6 +197,8 @@ def kernel_tables(dtype, dims, d: int = 0, m=4, sigma: float = 2.0, kernel=None,
     mode = kernel_evalmode if kernel_evalmode is not None else (FastApproximation() if kernel.name == "es" else Direct())
     o = build_opts(lib, dims, dtype.is_complex, real_dtype, M, sigma, kernel, mode if isinstance(mode, str) else mode.name, 1, fftshift,
                    False, "auto", None, 0, None, None, False, 0)
+    if not 0 <= d < len(dims):
+        raise ArgumentError(f"dimension {d} out of range")
     nk = dims[d] // 2 + 1 if (not dtype.is_complex and d == 0) else dims[d]
     shape, dx, os_dim = C.c_double(), C.c_double(), C.c_int64()
     cs = np.zeros((M + 4, 2 * M), dtype=np.float64)

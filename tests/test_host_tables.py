@@ -57,3 +57,31 @@ def test_es_kernel_refuses_direct_evaluation_without_a_gpu():
     import torch
     with pytest.raises(nb.ArgumentError):
         nb.kernel_tables(torch.complex64, (32, 32), 0, kernel=nb.ESKernel(), kernel_evalmode=nb.Direct())
+
+
+def test_argument_errors_of_the_reference_without_a_gpu():
+    """The option checks run before any device is touched (host_plan.cu: plan_sizes): the reference's ArgumentError cases —
+    oversampled size below the kernel support (src/plan.jl:545-556, test/errors.jl), sigma < 1, fftshift with real data —
+    are raised as ArgumentError by the same code path that creates plans."""
+    import torch
+    with pytest.raises(nb.ArgumentError, match="too small"):
+        nb.kernel_tables(torch.float64, (6,), 0, m=8, sigma=1.25, kernel=nb.KaiserBesselKernel())
+    with pytest.raises(nb.ArgumentError, match="sigma"):
+        nb.kernel_tables(torch.complex64, (32, 32), 0, m=4, sigma=0.9, kernel=nb.KaiserBesselKernel())
+    with pytest.raises(nb.ArgumentError, match="fftshift"):
+        nb.kernel_tables(torch.float32, (32, 32), 0, m=4, sigma=2.0, kernel=nb.KaiserBesselKernel(), fftshift=True)
+    with pytest.raises(nb.ArgumentError, match="out of range"):
+        nb.kernel_tables(torch.complex64, (32, 32), 2, m=4, sigma=2.0, kernel=nb.KaiserBesselKernel())
+
+
+def test_oversampled_sizes_follow_the_reference_rule_without_a_gpu():
+    """Ñ = nextprod((2, 3, 5), floor(sigma N)) with sigma converted to T first (src/plan.jl:575-576, 485-498); real data: the first
+    dimension is rounded on N/2 and doubled."""
+    import torch
+    for T, tdt in ((np.float32, torch.float32), (np.float64, torch.float64), (np.complex64, torch.complex64)):
+        for dims, sigma in (((48, 40), 1.5), ((97, 33), 1.25), ((256,), 2.0), ((30, 30, 30), 1.1)):
+            op = OraclePlan(T, dims, m=2, sigma=sigma)
+            for d in range(len(dims)):
+                kt = nb.kernel_tables(tdt, dims, d, m=2, sigma=sigma, kernel=nb.BackwardsKaiserBesselKernel(),
+                                      kernel_evalmode=nb.FastApproximation())
+                assert kt["os_dim"] == op.Nos[d], (T, dims, sigma, d)
