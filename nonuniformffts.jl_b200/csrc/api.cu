@@ -411,7 +411,8 @@ int nufft_describe(nufft_plan h, char *buf, size_t buflen)
              g.B[0], g.B[1], g.B[2], 2 * p.M - 1, (long long)p.nbins,
              p.method == NUFFT_METHOD_SHARED_MEMORY ? "shared_memory" : "global_memory",
              p.pfft ? "pruned 1-D passes fused with deconvolution (pfft.cu)" : "cuFFT + separate deconvolution",
-             g.T[0], g.T[1], g.T[2], g.S[0], g.batch, g.chunk, g.rt == 3 ? ", column-streaming kernels" : "");
+             g.T[0], g.T[1], g.T[2], g.S[0], g.batch, g.chunk,
+             g.rt == 3 ? (p.cplx ? ", ring-window register kernels" : ", column-streaming register kernels") : "");
     return NUFFT_SUCCESS;
 }
 
