@@ -385,7 +385,7 @@ static inline int64_t mg_grown(int64_t need) { return need + need / 8 + 1024; }
 
 static int mg_ensure_user(Mgpu &m, MgRank &R, int64_t np)
 {
-    if (np <= R.cap_user) return NUFFT_SUCCESS;
+    if (np <= R.cap_user && R.cap_user > 0) return NUFFT_SUCCESS;          // (a rank without points still owns minimal buffers: they are windows)
     auto f = [](auto *&p) { if (p) { cudaFree((void *)p); p = nullptr; } };
     f(R.d_sendperm); f(R.d_sv);
     for (int d = 0; d < 3; ++d) f(R.d_sx[d]);
@@ -400,7 +400,7 @@ static int mg_ensure_user(Mgpu &m, MgRank &R, int64_t np)
 
 static int mg_ensure_slab(Mgpu &m, MgRank &R, int64_t np)
 {
-    if (np <= R.cap_slab) return NUFFT_SUCCESS;
+    if (np <= R.cap_slab && R.cap_slab > 0) return NUFFT_SUCCESS;
     auto f = [](auto *&p) { if (p) { cudaFree((void *)p); p = nullptr; } };
     f(R.d_rv);
     for (int d = 0; d < 3; ++d) f(R.d_rx[d]);
@@ -700,8 +700,8 @@ static int slab_set_points(Mgpu &m, const int64_t np[], const void *const x[])
         for (int r = 0; r < G; ++r) {
             int64_t row = 0, col = 0;
             for (int t = 0; t < G; ++t) { row += (int64_t)cm[(size_t)r * MG_MAX_RANKS + t]; col += (int64_t)cm[(size_t)t * MG_MAX_RANKS + r]; }
-            if (row > m.cap_user_all[r]) { m.cap_user_all[r] = mg_grown(row); remap = true; }
-            if (col > m.cap_slab_all[r]) { m.cap_slab_all[r] = mg_grown(col); remap = true; }
+            if (row > m.cap_user_all[r] || m.cap_user_all[r] == 0) { m.cap_user_all[r] = mg_grown(row); remap = true; }
+            if (col > m.cap_slab_all[r] || m.cap_slab_all[r] == 0) { m.cap_slab_all[r] = mg_grown(col); remap = true; }
         }
         if (remap) {
             mg_win_close(m, W_DYNAMIC);
