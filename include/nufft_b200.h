@@ -122,12 +122,12 @@ int  nufft_plan_destroy(nufft_plan plan);
 int  nufft_plan_shape(nufft_plan plan, int64_t size_out[3], int64_t os_dims[3], int32_t *ntransforms);
 
 /* kernel data for parity tests: shape parameter (beta or tau), dx, the (M+4)x2M polynomial
- * coefficients [p][j] and the Fourier coefficients phihat_d (src/Kernels/*.jl). Host output. */
+ * coefficients [p][j] and the Fourier coefficients phihat_d (src/Kernels/<kernel>.jl). Host output. */
 int  nufft_plan_kernel_info(nufft_plan plan, int32_t d, double *shape_param, double *dx,
                             double *cs_host /* (M+4)*2M or NULL */, double *phihat_host /* size(p)[d] or NULL */);
 
 /* The same kernel data WITHOUT a plan and without touching a device: what a plan created from `opts` would hold for dimension d
- * (optimal_kernel + the *KernelData constructors, src/Kernels/*.jl; phihat over the kept wavenumbers, src/plan.jl:503-512).
+ * (optimal_kernel + the *KernelData constructors, src/Kernels/<kernel>.jl; phihat over the kept wavenumbers, src/plan.jl:503-512).
  * cs_len >= (M+4)*2M, phihat_len >= size(p)[d]; any output pointer may be NULL.  Lets CPU-only tests compare the library's tables
  * with the oracle's. */
 int  nufft_kernel_tables(const nufft_opts *opts, int32_t d, double *shape_param, double *dx, int64_t *os_dim,

@@ -2,6 +2,8 @@
 and the ctypes structs mirror the C structs."""
 import ctypes as C
 import re
+
+import pytest
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -85,3 +87,20 @@ def test_mgpu_argument_validation_without_a_gpu():
     assert lib.nufft_mgpu_destroy(None) == 0
     assert lib.nufft_mgpu_synchronize(None) == _lib.NUFFT_ERR_STATE
     assert _lib.MGPU_STRATEGIES == {"auto": 0, "slab": 1, "points": 2, "transforms": 3}
+
+
+def test_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/nufft_b200.h must compile as C99 without warnings (no C++, no torch types)."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = Path(__file__).resolve().parent.parent
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "nufft_b200.h"\nint main(void) { nufft_opts o; nufft_callbacks c; (void)o; (void)c; '
+                   'return NUFFT_KERNEL_ES == 4 && NUFFT_MGPU_SLAB == 1 ? 0 : 1; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(root / "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
